@@ -268,6 +268,12 @@ class Tree:
                                                      ("nnodes", "parent", "action", "child", "order", "nchild", "expanded", "prior", "q", "visits", "policy", "states")])
         return d
 
+    def poke(self, g: int, node: int, prior, q, visits, child_order):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        pr, qq, vv = f(prior), f(q), f(visits)
+        co = np.ascontiguousarray(child_order, dtype=np.int32)
+        lib().orc_tree_poke(self._h, C.c_int64(g), node, _p(pr), _p(qq), _p(vv), _p(co), len(co))
+
     def counters(self):
         out = np.zeros(4, dtype=np.int64)
         lib().orc_get_counters(self._h, _p(out))

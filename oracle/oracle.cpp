@@ -1031,6 +1031,26 @@ int orc_tree_dump(void* tp, int64_t L, int32_t* nnodes, int32_t* parent, int32_t
   }
   return 0;
 }
+// Test hook: overwrite the statistics of node `node` (1-based) of game g and create its children in
+// the given action order, as if those descents/backups had happened (used by the α-solve KAT).
+int orc_tree_poke(void* tp, int64_t g, int node, const float* prior, const float* q, const float* visits,
+                  const int32_t* child_order, int nchild) {
+  Tree* t = (Tree*)tp; const int A = t->s.A;
+  for (int a = 0; a < A; a++) {
+    t->prior[t->i3(a, node - 1, g)] = prior[a]; t->q[t->i3(a, node - 1, g)] = q[a]; t->visits[t->i3(a, node - 1, g)] = visits[a];
+    t->policy[t->i3(a, node - 1, g)] = prior[a];
+  }
+  for (int k = 0; k < nchild; k++) {
+    int a = child_order[k];
+    t->newindex[g] += 1; int ni = t->newindex[g];
+    t->childnbr[t->i2(node - 1, g)] += 1; int cn = t->childnbr[t->i2(node - 1, g)];
+    t->childID[t->ic(cn - 1, node - 1, g)] = ni; t->Achild[t->i3(a - 1, node - 1, g)] = cn;
+    t->parent[t->i2(ni - 1, g)] = node; t->actionFromParent[t->i2(ni - 1, g)] = a;
+    t->state[t->i2(ni - 1, g)] = play(t->s, t->state[t->i2(node - 1, g)], a);
+  }
+  t->expanded[t->i2(node - 1, g)] = 1; t->uptodate[t->i2(node - 1, g)] = 0;
+  return 0;
+}
 int orc_get_counters(void* tp, int64_t* out4) {
   Tree* t = (Tree*)tp; out4[0] = t->cnt_descents; out4[1] = t->cnt_nodes_traversed; out4[2] = t->cnt_newton_solves; out4[3] = t->cnt_newton_iters; return 0;
 }
