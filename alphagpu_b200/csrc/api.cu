@@ -1,0 +1,182 @@
+// api.cu — the C ABI of include/alphagpu.h: argument checking and run-time dispatch on the game plugin.
+#include <mutex>
+
+#include "engine.cuh"
+
+using namespace ag;
+
+struct agpu_ctx {
+  EngineBase* eng;
+};
+
+static thread_local std::string g_create_error;
+
+namespace ag {
+__global__ void debug_expf_kernel(const float* x, long long n, float* y, int sigmoid) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = sigmoid ? c_sigmoidf(x[i]) : c_expf(x[i]);
+}
+}  // namespace ag
+
+static bool fill_info(int32_t game, int32_t n, int32_t nvict, agpu_game_info* o) {
+  switch (game) {
+    case AGPU_CONNECT4: *o = {7, 42, 42, 42, 104}; return true;                                   // 4IARow.jl:6-12
+    case AGPU_GOBANG:                                                                              // Gobang.jl:8-11
+      if (n < 1 || n * n > 192 || nvict < 2 || nvict > n) return false;
+      *o = {n * n, n * n, n * n, n * n, 104}; return true;
+    case AGPU_HEX:                                                                                 // Hex.jl:8-11
+      if (n < 2 || (n + 1) * (n + 1) > 192) return false;
+      *o = {n * n, (n + 1) * (n + 1), (n + 1) * (n + 1), n * n, 104}; return true;
+    case AGPU_REVERSI8: *o = {65, 64, 64, 70, 152}; return true;                                   // Reversi8x8.jl:5-8
+    case AGPU_REVERSI6: *o = {37, 36, 36, 50, 152}; return true;                                   // Reversi6x6.jl:6-9
+  }
+  return false;
+}
+
+extern "C" {
+
+int agpu_abi_version(void) { return AGPU_ABI_VERSION; }
+
+int agpu_game_info_get(int32_t game, int32_t n, int32_t nvict, agpu_game_info* out) {
+  if (!out) return AGPU_ERR_INVALID;
+  return fill_info(game, n, nvict, out) ? AGPU_OK : AGPU_ERR_INVALID;
+}
+
+int agpu_create(agpu_ctx** out, const agpu_config* cfg) {
+  if (!out || !cfg) { g_create_error = "null argument"; return AGPU_ERR_INVALID; }
+  *out = nullptr;
+  agpu_game_info info;
+  if (!fill_info(cfg->game, cfg->n, cfg->nvict, &info)) { g_create_error = "unknown game or board size"; return AGPU_ERR_INVALID; }
+  EngineBase* e = nullptr;
+  switch (cfg->game) {
+    case AGPU_CONNECT4: e = make_engine_connect4(); break;
+    case AGPU_GOBANG: e = make_engine_gobang(cfg->n, cfg->nvict); break;
+    case AGPU_HEX: e = make_engine_hex(cfg->n); break;
+    case AGPU_REVERSI8: e = make_engine_reversi(8); break;
+    case AGPU_REVERSI6: e = make_engine_reversi(6); break;
+  }
+  if (!e) {
+    g_create_error = "this (game, n, nvict) is not compiled in; see AG_GOBANG_SIZES / AG_HEX_SIZES in engine_games.cu";
+    return AGPU_ERR_INVALID;
+  }
+  e->cfg = *cfg;
+  e->info = info;
+  int rc = e->init();
+  if (rc != AGPU_OK) { g_create_error = e->err; delete e; return rc; }
+  *out = new agpu_ctx{e};
+  return AGPU_OK;
+}
+
+void agpu_destroy(agpu_ctx* ctx) {
+  if (!ctx) return;
+  delete ctx->eng;
+  delete ctx;
+}
+
+const char* agpu_last_error(const agpu_ctx* ctx) { return ctx ? ctx->eng->err.c_str() : g_create_error.c_str(); }
+
+#define CTX_OR_FAIL() \
+  if (!ctx) return AGPU_ERR_INVALID;
+
+int agpu_set_weights(agpu_ctx* ctx, int32_t slot, const float* base, const float* const* res, const float* pol_w, const float* pol_b,
+                     const float* val_w, const float* val_b) {
+  CTX_OR_FAIL();
+  return ctx->eng->set_weights(slot, base, res, pol_w, pol_b, val_w, val_b);
+}
+int agpu_forward(agpu_ctx* ctx, int32_t slot, const float* x, int64_t L, float* logits, float* value) {
+  CTX_OR_FAIL();
+  return ctx->eng->forward(slot, x, L, logits, value);
+}
+int agpu_position_init(agpu_ctx* ctx, void* positions_out, int64_t n) {
+  CTX_OR_FAIL();
+  return ctx->eng->position_init(positions_out, n);
+}
+int agpu_can_play(agpu_ctx* ctx, const void* positions, int64_t n, uint8_t* legal) {
+  CTX_OR_FAIL();
+  if (!legal) return AGPU_ERR_INVALID;
+  return ctx->eng->game_ops(positions, nullptr, n, nullptr, legal, nullptr, nullptr, nullptr);
+}
+int agpu_play(agpu_ctx* ctx, const void* positions, const int32_t* actions, int64_t n, void* positions_out) {
+  CTX_OR_FAIL();
+  if (!positions_out || !actions) return AGPU_ERR_INVALID;
+  return ctx->eng->game_ops(positions, actions, n, positions_out, nullptr, nullptr, nullptr, nullptr);
+}
+int agpu_is_over(agpu_ctx* ctx, const void* positions, int64_t n, uint8_t* over, int8_t* result) {
+  CTX_OR_FAIL();
+  if (!over || !result) return AGPU_ERR_INVALID;
+  return ctx->eng->game_ops(positions, nullptr, n, nullptr, nullptr, over, result, nullptr);
+}
+int agpu_encode(agpu_ctx* ctx, const void* positions, int64_t n, float* batch) {
+  CTX_OR_FAIL();
+  if (!batch) return AGPU_ERR_INVALID;
+  return ctx->eng->game_ops(positions, nullptr, n, nullptr, nullptr, nullptr, nullptr, batch);
+}
+int agpu_reinit(agpu_ctx* ctx, const void* positions, int64_t L, const uint32_t* uids) {
+  CTX_OR_FAIL();
+  return ctx->eng->reinit(positions, L, uids);
+}
+int agpu_search(agpu_ctx* ctx, int64_t L, int32_t slot, int32_t visits, int32_t training, float cpuct, float noise, const float* prob,
+                uint64_t seed, uint32_t ply) {
+  CTX_OR_FAIL();
+  (void)noise;   // parsed and ignored by the reference as well (mcts_gpu.jl:250,273)
+  return ctx->eng->search(L, slot, visits, training, cpuct, prob, seed, ply);
+}
+int agpu_get_roots(agpu_ctx* ctx, int64_t L, float* policy_final, float* batch) {
+  CTX_OR_FAIL();
+  return ctx->eng->get_roots(L, policy_final, batch);
+}
+int agpu_search_begin(agpu_ctx* ctx, int64_t L) {
+  CTX_OR_FAIL();
+  return ctx->eng->search_begin(L);
+}
+int agpu_select(agpu_ctx* ctx, int64_t L, int32_t rollout, int32_t last_rollout, float cpuct, const float* prob, uint64_t seed, uint32_t ply) {
+  CTX_OR_FAIL();
+  return ctx->eng->select(L, rollout, last_rollout, cpuct, prob, seed, ply);
+}
+int agpu_get_leaves(agpu_ctx* ctx, int64_t L, int32_t* leaf, float* batch) {
+  CTX_OR_FAIL();
+  return ctx->eng->get_leaves(L, leaf, batch);
+}
+int agpu_eval(agpu_ctx* ctx, int64_t L, int32_t slot, float* logits, float* value) {
+  CTX_OR_FAIL();
+  return ctx->eng->eval(L, slot, logits, value);
+}
+int agpu_expand_backup(agpu_ctx* ctx, int64_t L, int32_t training, int32_t last_rollout, const float* prior, const float* value) {
+  CTX_OR_FAIL();
+  return ctx->eng->expand_backup(L, training, last_rollout, prior, value);
+}
+int agpu_get_tree(agpu_ctx* ctx, int64_t L, agpu_tree_dump* out) {
+  CTX_OR_FAIL();
+  return ctx->eng->get_tree(L, out);
+}
+int agpu_selfplay(agpu_ctx* ctx, int32_t slot, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct, float noise, uint64_t seed,
+                  agpu_samples* samples, int64_t results[3], agpu_run_stats* stats) {
+  CTX_OR_FAIL();
+  (void)noise;
+  return ctx->eng->selfplay(slot, visits, ngames, uid_base, cpuct, seed, samples, results, stats, false, 0);
+}
+int agpu_duel(agpu_ctx* ctx, int32_t slot_a, int32_t slot_b, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct, uint64_t seed,
+              int64_t results[3], agpu_run_stats* stats) {
+  CTX_OR_FAIL();
+  return ctx->eng->selfplay(slot_a, visits, ngames, uid_base, cpuct, seed, nullptr, results, stats, true, slot_b);
+}
+int agpu_profile(agpu_ctx* ctx, int32_t enable) {
+  CTX_OR_FAIL();
+  return ctx->eng->profile(enable);
+}
+int agpu_get_kernel_times(agpu_ctx* ctx, agpu_kernel_times* out, int32_t reset) {
+  CTX_OR_FAIL();
+  return ctx->eng->kernel_times(out, reset);
+}
+int agpu_layout_info(agpu_ctx* ctx, int64_t* node_bytes, int64_t* game_bytes, int64_t* lanes_per_game) {
+  CTX_OR_FAIL();
+  return ctx->eng->layout_info(node_bytes, game_bytes, lanes_per_game);
+}
+/* test hook: the canonical exp / sigmoid evaluated on the device */
+int agpu_debug_expf(agpu_ctx* ctx, const float* x, int64_t n, float* y, int32_t sigmoid) {
+  CTX_OR_FAIL();
+  if (!x || !y || n < 1) return AGPU_ERR_INVALID;
+  return ctx->eng->debug_expf(x, n, y, sigmoid);
+}
+
+}  // extern "C"

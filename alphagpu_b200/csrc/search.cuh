@@ -1,0 +1,577 @@
+// search.cuh — tree layout in HBM and the search kernels (select / expand+backup / ply bookkeeping).
+//
+// Replaces kdescendTree!, expand, backUp, copy_pol, reinit and the per-ply fills of mcts_gpu.jl
+// (:100-199, :250-339, :359-387).  Results are bit-identical to a sequential IEEE-fp32 reading of those
+// functions (the CPU oracle); what changes is where the work runs:
+//
+//  * Layout.  One contiguous block of R node records per game; a record holds, struct-of-arrays over the
+//    (padded) actions, prior f32 | q f32 | visits u16 | child u8 | order u8, then the packed State and an
+//    8-byte header.  Connect4: exactly one 128-byte line per node.  The reference's Achild/childID double
+//    indirection (R*R int64 per game) becomes child[a] (node id) + order[slot] (action, creation order);
+//    `policy`, `uptodate`, `expanded` arrays disappear (π̄ is recomputed from q/visits when a node has
+//    visits — the reference's sticky-dirty rule, mcts_gpu.jl:114,321 — and flags live in the header).
+//  * Mapping.  W = min(32, pow2ceil(A)) lanes cooperate on one game (Connect4: 8 lanes, 4 games per warp):
+//    lane l owns actions l, l+W, …  Loads of a node's statistics are one coalesced segment per field.
+//    Divisions/sqrt of the α-solve run lane-parallel; every order-sensitive fp32 sum is then accumulated
+//    by broadcast in the reference's order (ascending action; Newton terms in child-creation order), so
+//    parallelism never changes a rounding.
+//  * No per-ply memset: a node's q/visits/child are zeroed when the node is allocated.
+#pragma once
+#include "games.cuh"
+
+namespace ag {
+
+enum : uint8_t { F_EXPANDED = 1, F_TERMINAL = 2 };
+
+struct NodeHdr {
+  uint8_t parent;   // 1-based node id, 0 = root has none            (vnodes.parent)
+  uint8_t action;   // 1-based action from parent                    (vnodes.actionFromParent)
+  uint8_t nchild;   //                                               (vnodesStats.childnbr)
+  uint8_t flags;    // F_EXPANDED (vnodes.expanded) | F_TERMINAL (isOver cached at creation)
+  int8_t result;    // winner colour if terminal
+  uint8_t pad[3];
+};
+static_assert(sizeof(NodeHdr) == 8, "header");
+
+constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+template <class G>
+struct Layout {
+  static constexpr int A = G::A;
+  static constexpr int W = pow2ceil(A) < 32 ? pow2ceil(A) : 32;   // lanes per game
+  static constexpr int APL = (A + W - 1) / W;                      // actions per lane
+  static constexpr int APAD = W * APL;
+  static constexpr int GPW = 32 / W;                               // games per warp
+  static constexpr int OFF_PRIOR = 0;
+  static constexpr int OFF_Q = 4 * APAD;
+  static constexpr int OFF_VIS = 8 * APAD;
+  static constexpr int OFF_CHILD = 10 * APAD;
+  static constexpr int OFF_ORDER = 11 * APAD;
+  static constexpr int OFF_STATE = (12 * APAD + 7) / 8 * 8;
+  static constexpr int OFF_HDR = OFF_STATE + (int)sizeof(typename G::State);
+  static constexpr int REC = (OFF_HDR + 8 + 31) / 32 * 32;         // record size, multiple of a 32 B sector
+  static constexpr int OUTS = (A + 1 + 3) / 4 * 4;                 // floats per game of network output: logits[A], value
+  static_assert(sizeof(typename G::State) % 8 == 0, "state alignment");
+};
+
+struct SearchParams {
+  char* tree;            // [L][R] node records
+  size_t game_stride;    // R * REC
+  int R;
+  int32_t* nnodes;       // [L]  newindex
+  int32_t* leaf;         // [L]  0-based leaf node
+  uint32_t* uid;         // [L]  global game id (RNG key)
+  float* policy_final;   // [L][A]
+  float* nn_out;         // [L][OUTS] logits then value
+  unsigned long long* counters;   // [2] nodes traversed, descents (profiling; may be null)
+};
+
+template <int W> AG_D unsigned group_mask() {
+  return W == 32 ? 0xffffffffu : (((1u << W) - 1u) << ((threadIdx.x & 31) & ~(W - 1)));
+}
+template <int W> AG_D float gshfl(unsigned m, float v, int src) { return __shfl_sync(m, v, src, W); }
+template <int W> AG_D int gshfl(unsigned m, int v, int src) { return __shfl_sync(m, v, src, W); }
+template <int W> AG_D float gmax(unsigned m, float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(m, v, o, W));
+  return v;
+}
+template <int W> AG_D int gsum(unsigned m, int v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o, W);
+  return v;
+}
+template <int W> AG_D int gcount(unsigned m, bool pred) { return __popc(__ballot_sync(m, pred) & m); }
+
+// value of slot j (uniform across the group) out of a small per-lane array, without dynamic register indexing
+template <int APL, class T> AG_D T pick(const T (&v)[APL], int j) {
+  T r = v[0];
+#pragma unroll
+  for (int k = 1; k < APL; k++) if (j == k) r = v[k];
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// root install: re_init (mcts_gpu.jl:359-373) + the fills of mcts_single (:380-387) for node 1 only.
+// src == null keeps the stored root state (agpu_search_begin).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+__global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, const typename G::State* __restrict__ src,
+                                                         const uint32_t* __restrict__ uid) {
+  typedef Layout<G> Lay;
+  int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= L) return;
+  char* rec = P.tree + (size_t)g * P.game_stride;
+  if (src) *reinterpret_cast<typename G::State*>(rec + Lay::OFF_STATE) = src[g];
+  if (uid) P.uid[g] = uid[g];
+  uint4 z = make_uint4(0, 0, 0, 0);
+  // zero prior|q|visits|child|order (12*APAD bytes, APAD multiple of... at least 1): word stores
+  for (int o = 0; o + 16 <= Lay::OFF_STATE; o += 16) *reinterpret_cast<uint4*>(rec + o) = z;
+  for (int o = Lay::OFF_STATE / 16 * 16; o < Lay::OFF_STATE; o += 4) *reinterpret_cast<uint32_t*>(rec + o) = 0;
+  NodeHdr h; h.parent = 0; h.action = 0; h.nchild = 0; h.flags = 0; h.result = 0; h.pad[0] = h.pad[1] = h.pad[2] = 0;
+  *reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR) = h;
+  P.nnodes[g] = 1;
+  P.leaf[g] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// select: kdescendTree! (mcts_gpu.jl:100-199).  One group of W lanes per game.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+__global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int rollout, int last_rollout, float cpuct,
+                                                     const float* __restrict__ prob, u64 seed, u32 ply) {
+  typedef Layout<G> Lay;
+  constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  const int l = threadIdx.x & (W - 1);
+  if (g >= L) return;
+  const unsigned gm = group_mask<W>();
+  char* gbase = P.tree + (size_t)g * P.game_stride;
+  int nn = P.nnodes[g];
+  const u32 uid = P.uid[g];
+  int node = 0, depth = 0, rblock = -1;
+  Philox4 rnd; rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
+
+  while (true) {
+    char* rec = gbase + (size_t)node * REC;
+    const NodeHdr h = *reinterpret_cast<const NodeHdr*>(rec + Lay::OFF_HDR);
+    if (!(h.flags & F_EXPANDED)) break;                                   // while expanded[nindex]==1  (:110)
+
+    float p[APL], q[APL], pol[APL];
+    int vis[APL], ch[APL], ord[APL];
+#pragma unroll
+    for (int j = 0; j < APL; j++) {
+      const int a = j * W + l;
+      const bool in = a < A;
+      p[j] = in ? *reinterpret_cast<const float*>(rec + Lay::OFF_PRIOR + 4 * a) : 0.f;
+      q[j] = in ? *reinterpret_cast<const float*>(rec + Lay::OFF_Q + 4 * a) : 0.f;
+      vis[j] = in ? (int)*reinterpret_cast<const uint16_t*>(rec + Lay::OFF_VIS + 2 * a) : 0;
+      ch[j] = in ? (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_CHILD + a) : 0;
+      ord[j] = in ? (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_ORDER + a) : 0;
+    }
+    int nv = 0;
+#pragma unroll
+    for (int j = 0; j < APL; j++) nv += vis[j];
+    nv = gsum<W>(gm, nv);
+
+    if (nv > 0) {                                                          // uptodate != 1  (:114): some backup passed through
+      // n = 1 + Σ visits (exact), prior_rem = Σ_{no child} prior in ascending action order, A = #{prior > 0}   (:116-131)
+      const float n = (float)(1 + nv);
+      float rem = 0.f;
+      int acount = 0;
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        const float contrib = (ch[j] == 0) ? p[j] : 0.f;
+        acount += gcount<W>(gm, p[j] > 0.f);
+#pragma unroll
+        for (int s = 0; s < W; s++) {
+          if (j * W + s < A) rem = fadd(rem, gshfl<W>(gm, contrib, s));
+        }
+      }
+      const float lambda = fdiv(fmul(cpuct, fsqrt(n)), fadd((float)acount, n));   // :132
+      rem = fmul(rem, lambda);                                                       // :134
+      float alpha = 0.f;                                                             // :135-138
+      float top[APL];
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        top[j] = fmul(lambda, p[j]);
+        if (j * W + l < A) alpha = fmaxf(alpha, fadd(q[j], fmaxf(top[j], 1e-4f)));
+      }
+      alpha = gmax<W>(gm, alpha);
+      float err = __int_as_float(0x7f800000);
+      const int nchild = h.nchild;
+      for (int it = 0; it < 100; it++) {                                             // :141-162
+        float S = fdiv(rem, alpha);
+        float gs = fdiv(-rem, fmul(alpha, alpha));
+        float t1[APL], t2[APL];
+#pragma unroll
+        for (int j = 0; j < APL; j++) {
+          const float bot = fsub(alpha, q[j]);
+          t1[j] = fdiv(top[j], bot);
+          t2[j] = fdiv(-top[j], fmul(bot, bot));
+        }
+        for (int k = 0; k < nchild; k++) {                                           // children in creation (slot) order
+          const int a = gshfl<W>(gm, pick<APL>(ord, k / W), k % W) - 1;
+          S = fadd(S, gshfl<W>(gm, pick<APL>(t1, a / W), a % W));
+          gs = fadd(gs, gshfl<W>(gm, pick<APL>(t2, a / W), a % W));
+        }
+        const float newerr = fsub(S, 1.f);
+        if (newerr < 0.001f || newerr == err) break;
+        alpha = fsub(alpha, fdiv(newerr, gs));
+        err = newerr;
+      }
+#pragma unroll
+      for (int j = 0; j < APL; j++) pol[j] = fdiv(top[j], fsub(alpha, q[j]));      // :165-169
+    } else {
+#pragma unroll
+      for (int j = 0; j < APL; j++) pol[j] = p[j];                                  // policy == prior until the first backup (:297-299)
+    }
+
+    if (node == 0 && last_rollout) {                                                 // copy_pol (:330-339): π̄_root of the last descent
+#pragma unroll
+      for (int j = 0; j < APL; j++) if (j * W + l < A) P.policy_final[(size_t)g * A + j * W + l] = pol[j];
+    }
+
+    // uniform for this depth: injected prob[depth, game] (:178) or Philox
+    float u;
+    if (prob) u = prob[((size_t)rollout * L + g) * G::MAXLEN + depth];
+    else {
+      if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
+      const int w = depth & 3;
+      u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
+    }
+    // inverse-CDF scan in ascending action order (:172-182)
+    float cum = 0.f;
+    int best = -1;
+    bool done = false;
+#pragma unroll
+    for (int j = 0; j < APL; j++) {
+#pragma unroll
+      for (int s = 0; s < W; s++) {
+        if (j * W + s < A) {
+          const float d = gshfl<W>(gm, pol[j], s);
+          if (!done) {
+            cum = fadd(cum, d);
+            if (d > 0.f) best = j * W + s;
+            if (cum >= u) done = true;
+          }
+        }
+      }
+    }
+    if (best < 0) best = 0;
+    int c = gshfl<W>(gm, pick<APL>(ch, best / W), best % W);
+    if (c == 0) {                                                                     // allocate the child (:183-191)
+      nn += 1;
+      c = nn;
+      if (l == best % W) *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
+      const typename G::State ps = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+      const typename G::State ns = G::play(ps, best + 1);
+      int res = 0;
+      const bool term = G::is_over(ns, res);
+      char* nrec = gbase + (size_t)(c - 1) * REC;
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        const int a = j * W + l;
+        *reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * a) = 0.f;
+        *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * a) = 0;
+        *reinterpret_cast<uint8_t*>(nrec + Lay::OFF_CHILD + a) = 0;
+      }
+      if (l == 0) {
+        *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + h.nchild) = (uint8_t)(best + 1);
+        reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(h.nchild + 1);
+        *reinterpret_cast<typename G::State*>(nrec + Lay::OFF_STATE) = ns;
+        NodeHdr nh; nh.parent = (uint8_t)(node + 1); nh.action = (uint8_t)(best + 1); nh.nchild = 0;
+        nh.flags = term ? F_TERMINAL : 0; nh.result = (int8_t)res; nh.pad[0] = nh.pad[1] = nh.pad[2] = 0;
+        *reinterpret_cast<NodeHdr*>(nrec + Lay::OFF_HDR) = nh;
+      }
+      node = c - 1;
+      depth += 1;
+      break;                                                                           // a new node is unexpanded: the while ends
+    }
+    node = c - 1;                                                                      // :192
+    depth += 1;
+  }
+  if (l == 0) {
+    P.leaf[g] = node;                                                                  // :195
+    P.nnodes[g] = nn;
+    if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)depth); atomicAdd(&P.counters[1], 1ull); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// expand + backUp (mcts_gpu.jl:250-328), with softmax! (:417) when the prior comes from the network.
+// INJECT: prior_in[L][A] is already softmaxed (what `expand` receives), value_in[L].
+// ------------------------------------------------------------------------------------------------
+template <class G, bool INJECT>
+__global__ void __launch_bounds__(256) expand_backup_kernel(SearchParams P, int L, int training, int last_rollout,
+                                                            const float* __restrict__ prior_in, const float* __restrict__ value_in) {
+  typedef Layout<G> Lay;
+  constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  const int l = threadIdx.x & (W - 1);
+  if (g >= L) return;
+  const unsigned gm = group_mask<W>();
+  char* gbase = P.tree + (size_t)g * P.game_stride;
+  const int leaf = P.leaf[g];
+  char* rec = gbase + (size_t)leaf * REC;
+  const NodeHdr h = *reinterpret_cast<const NodeHdr*>(rec + Lay::OFF_HDR);
+  const typename G::State st = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+  const bool term = (h.flags & F_TERMINAL) != 0;
+  float v = 0.f;
+
+  if (!term) {                                                                         // expand: :258-296
+    float pin[APL];
+    if (INJECT) {
+#pragma unroll
+      for (int j = 0; j < APL; j++) { const int a = j * W + l; pin[j] = a < A ? prior_in[(size_t)g * A + a] : 0.f; }
+      v = value_in[g];
+    } else {
+      const float* o = P.nn_out + (size_t)g * Lay::OUTS;
+      float x[APL];
+      float m = -__int_as_float(0x7f800000);
+#pragma unroll
+      for (int j = 0; j < APL; j++) { const int a = j * W + l; x[j] = a < A ? o[a] : 0.f; if (a < A) m = fmaxf(m, x[j]); }
+      m = gmax<W>(gm, m);
+      float e[APL];
+      float ssum = 0.f;
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        e[j] = (j * W + l < A) ? c_expf(fsub(x[j], m)) : 0.f;
+#pragma unroll
+        for (int s = 0; s < W; s++) if (j * W + s < A) ssum = fadd(ssum, gshfl<W>(gm, e[j], s));
+      }
+#pragma unroll
+      for (int j = 0; j < APL; j++) pin[j] = fdiv(e[j], ssum);
+      v = o[A];
+    }
+    bool legal[APL];
+    float normalize = 0.f;
+    int acount = 0;
+#pragma unroll
+    for (int j = 0; j < APL; j++) {
+      const int a = j * W + l;
+      legal[j] = a < A && G::can_play(st, a + 1);
+      const float contrib = legal[j] ? pin[j] : 0.f;
+      acount += gcount<W>(gm, legal[j]);
+#pragma unroll
+      for (int s = 0; s < W; s++) if (j * W + s < A) normalize = fadd(normalize, gshfl<W>(gm, contrib, s));
+    }
+    const bool rootmix = (leaf == 0) && training;                                       // :259-275
+    const float unif = fdiv(0.25f, (float)acount);
+#pragma unroll
+    for (int j = 0; j < APL; j++) {
+      const int a = j * W + l;
+      float pr = 0.f;
+      if (legal[j]) pr = rootmix ? fadd(fdiv(fmul(0.75f, pin[j]), normalize), unif) : fdiv(pin[j], normalize);
+      *reinterpret_cast<float*>(rec + Lay::OFF_PRIOR + 4 * a) = pr;
+      if (leaf == 0 && last_rollout && a < A) P.policy_final[(size_t)g * A + a] = pr;    // R == 1: policy[:,1] is the prior itself
+    }
+    if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
+  }
+
+  // backUp: :306-328
+  int nindex = h.parent;
+  int move = h.action;
+  if (term) {
+    // value = (1 + player*r)/2 is a Float64 in the reference (:314): the running mean on this path is evaluated in double
+    double value = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;
+    while (nindex != 0) {
+      char* nrec = gbase + (size_t)(nindex - 1) * REC;
+      if (l == ((move - 1) % W)) {
+        float* qp = reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * (move - 1));
+        uint16_t* vp = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * (move - 1));
+        const float vf = (float)*vp;
+        const float prod = fmul(vf, *qp);
+        const float den = fadd(vf, 1.f);
+        *qp = (float)__ddiv_rn(__dadd_rn((double)prod, __dsub_rn(1.0, value)), (double)den);
+        *vp = (uint16_t)(*vp + 1);
+      }
+      const NodeHdr nh = *reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR);
+      move = nh.action; nindex = nh.parent;
+      value = __dsub_rn(1.0, value);
+    }
+  } else {
+    float value = v;
+    while (nindex != 0) {
+      char* nrec = gbase + (size_t)(nindex - 1) * REC;
+      if (l == ((move - 1) % W)) {
+        float* qp = reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * (move - 1));
+        uint16_t* vp = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * (move - 1));
+        const float vf = (float)*vp;
+        *qp = fdiv(fadd(fmul(vf, *qp), fsub(1.f, value)), fadd(vf, 1.f));               // :319
+        *vp = (uint16_t)(*vp + 1);                                                       // :320
+      }
+      const NodeHdr nh = *reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR);
+      move = nh.action; nindex = nh.parent;                                              // :322-323
+      value = fsub(1.f, value);                                                          // :324
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// decoder / decoder_roots (mcts_gpu.jl:202-246) to fp32 for the API, one thread per (game, feature)
+// ------------------------------------------------------------------------------------------------
+template <class G>
+__global__ void encode_nodes_kernel(SearchParams P, int L, int use_leaf, float* __restrict__ batch) {
+  typedef Layout<G> Lay;
+  const int F = 2 * G::VS;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)L * F) return;
+  int g = (int)(t / F), j = (int)(t % F);
+  int node = use_leaf ? P.leaf[g] : 0;
+  const typename G::State* st = reinterpret_cast<const typename G::State*>(P.tree + (size_t)g * P.game_stride + (size_t)node * Lay::REC + Lay::OFF_STATE);
+  batch[t] = enc_bit<G>(*st, j) ? 1.f : 0.f;
+}
+
+// plugin surface on plain state arrays (agpu_can_play / agpu_play / agpu_is_over / agpu_encode)
+template <class G>
+__global__ void game_ops_kernel(const typename G::State* __restrict__ in, const int32_t* __restrict__ actions, int n,
+                                typename G::State* __restrict__ played, uint8_t* __restrict__ legal, uint8_t* __restrict__ over,
+                                int8_t* __restrict__ result, float* __restrict__ enc, int init_only) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (init_only) { played[i] = G::init(); return; }
+  const typename G::State s = in[i];
+  if (legal) for (int a = 1; a <= G::A; a++) legal[(size_t)i * G::A + a - 1] = G::can_play(s, a) ? 1 : 0;
+  if (played) played[i] = G::play(s, actions[i]);
+  if (over) { int r = 0; bool f = G::is_over(s, r); over[i] = f ? 1 : 0; result[i] = (int8_t)r; }
+  if (enc) for (int j = 0; j < 2 * G::VS; j++) enc[(size_t)i * 2 * G::VS + j] = enc_bit<G>(s, j) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ply bookkeeping of the self-play / duel loops (mcts_gpu.jl:506-561, 600-639), one thread per game.
+// ------------------------------------------------------------------------------------------------
+struct SampleBufs {          // device SoA (Game.Sample, main4IARow.jl:29-37)
+  int8_t* state; float* policy; int8_t* player; float* value; int8_t* fstate; int32_t* game; int32_t* ply;
+  long long capacity;
+};
+struct PlyState {
+  void* next_state;          // [L] State after the move
+  uint8_t* alive;            // [L] 1 = game continues
+  int32_t* block_count;      // [blocks] survivors per block
+  int8_t* game_result;       // [ngames] winner colour
+  void* game_final;          // [ngames] final State (for fstate)
+  unsigned long long* tallies;  // [0..2] v,n,d  [3] total_length  [4] faults
+};
+
+// StatsBase.sample over the non-zero weights (mcts_gpu.jl:518-521) / over all entries in the duel (:605-606);
+// argmax (first maximal index) afterwards (:523, :608).  Returns a 1-based action.
+template <class G, bool DUEL>
+AG_D int choose_move(const float* __restrict__ pol, u32 round, float u) {
+  constexpr int A = G::A;
+  if (round < (DUEL ? 15u : 25u)) {
+    float wsum = 0.f;
+    int last = A;
+    if (!DUEL) last = 1;
+    for (int c = 0; c < A; c++) {
+      const float w = pol[c];
+      if (DUEL) wsum = fadd(wsum, w);
+      else if (w != 0.f) { wsum = fadd(wsum, w); last = c + 1; }
+    }
+    const float t = fmul(u, wsum);
+    float cw = 0.f;
+    bool first = true;
+    for (int c = 0; c < A; c++) {
+      const float w = pol[c];
+      if (!DUEL && w == 0.f) continue;
+      if (first) { cw = w; first = false; } else cw = fadd(cw, w);
+      if (!(cw < t) || c + 1 == last) return c + 1;
+    }
+    return last;
+  }
+  int best = 0;
+  float bv = pol[0];
+  for (int c = 1; c < A; c++) if (pol[c] > bv) { bv = pol[c]; best = c; }
+  return best + 1;
+}
+
+template <class G, bool DUEL>
+__global__ void __launch_bounds__(256) finish_ply_kernel(SearchParams P, int L, u32 round, u64 seed, u32 uid_base, SampleBufs S,
+                                                         long long sample_base, PlyState Y) {
+  typedef Layout<G> Lay;
+  typedef typename G::State State;
+  constexpr int A = G::A;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  bool alive = false;
+  if (g < L) {
+    const State st = *reinterpret_cast<const State*>(P.tree + (size_t)g * P.game_stride + Lay::OFF_STATE);
+    const u32 uid = P.uid[g];
+    const float* pol = P.policy_final + (size_t)g * A;
+    if (!DUEL) {                                                                        // push_buffer (main4IARow.jl:49-63)
+      const long long row = sample_base + g;
+      if (row < S.capacity) {
+        for (int j = 0; j < 2 * G::VS; j++) S.state[row * 2 * G::VS + j] = enc_bit<G>(st, j) ? 1 : 0;
+        for (int a = 0; a < A; a++) S.policy[row * A + a] = pol[a];
+        S.player[row] = st.player;
+        S.game[row] = (int32_t)uid;
+        S.ply[row] = (int32_t)round;
+      }
+    }
+    const Philox4 r = philox4x32_10(uid, round, ROLLOUT_MOVE, 0u, (u32)seed, (u32)(seed >> 32));
+    const int c = choose_move<G, DUEL>(pol, round, u01(r.v[0]));
+    if (!G::can_play(st, c)) atomicAdd(&Y.tallies[4], 1ull);                             // "faute" (:526-529)
+    const State ns = G::play(st, c);                                                     // :530
+    int res = 0;
+    const bool f = G::is_over(ns, res);                                                  // :531
+    reinterpret_cast<State*>(Y.next_state)[g] = ns;
+    alive = !f;
+    if (f) {
+      const u32 local = uid - uid_base;
+      Y.game_result[local] = (int8_t)res;
+      reinterpret_cast<State*>(Y.game_final)[local] = ns;
+      atomicAdd(&Y.tallies[res == 1 ? 0 : (res == 0 ? 1 : 2)], 1ull);                   // :541-547
+      atomicAdd(&Y.tallies[3], (unsigned long long)round);                               // :535
+    }
+    Y.alive[g] = alive ? 1 : 0;
+  }
+  const int cnt = __syncthreads_count(alive);
+  if (threadIdx.x == 0) Y.block_count[blockIdx.x] = cnt;
+}
+
+// exclusive scan of the per-block survivor counts (<= 1024 blocks per pass, looped), total -> *total_out
+static __global__ void __launch_bounds__(1024) scan_blocks_kernel(int32_t* __restrict__ block_count, int nblocks, int32_t* __restrict__ total_out) {
+  __shared__ int sm[1024];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblocks; base += 1024) {
+    const int i = base + threadIdx.x;
+    const int v = i < nblocks ? block_count[i] : 0;
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      int t = threadIdx.x >= o ? sm[threadIdx.x - o] : 0;
+      __syncthreads();
+      sm[threadIdx.x] += t;
+      __syncthreads();
+    }
+    const int incl = sm[threadIdx.x];
+    if (i < nblocks) block_count[i] = carry + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry += incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = carry;
+}
+
+// order-preserving compaction (deleteat!, mcts_gpu.jl:550-553) fused with re_init of the next ply (:557-561)
+template <class G>
+__global__ void __launch_bounds__(256) compact_kernel(SearchParams P, int L, PlyState Y, typename G::State* __restrict__ state_out,
+                                                      uint32_t* __restrict__ uid_out) {
+  typedef typename G::State State;
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool alive = g < L && Y.alive[g];
+  // block-level exclusive prefix of `alive`
+  __shared__ int wsum[8];
+  const unsigned b = __ballot_sync(0xffffffffu, alive);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int inwarp = __popc(b & ((1u << lane) - 1u));
+  if (lane == 0) wsum[w] = __popc(b);
+  __syncthreads();
+  int off = Y.block_count[blockIdx.x];
+  for (int k = 0; k < w; k++) off += wsum[k];
+  if (alive) {
+    const int ng = off + inwarp;
+    state_out[ng] = reinterpret_cast<const State*>(Y.next_state)[g];
+    uid_out[ng] = P.uid[g];
+  }
+}
+
+// update_buffer (main4IARow.jl:65-75) for every sample once all games have ended
+template <class G>
+__global__ void finalize_samples_kernel(SampleBufs S, long long count, u32 uid_base, const int8_t* __restrict__ game_result,
+                                        const typename G::State* __restrict__ game_final) {
+  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= count || row >= S.capacity) return;
+  const u32 local = (u32)S.game[row] - uid_base;
+  const int res = game_result[local];
+  const int player = S.player[row];
+  S.value[row] = (float)((double)(1 + res * player) / 2.0);
+  const typename G::State fs = game_final[local];
+  for (int j = 0; j < G::FS; j++) {
+    const int f = bb_get0<typename G::Geo>(fs.bp, j) ? fs.player : -fs.player;           // decode (mcts_gpu.jl:464-474)
+    S.fstate[row * G::FS + j] = (int8_t)(f * player);
+  }
+}
+
+}  // namespace ag

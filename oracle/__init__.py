@@ -184,6 +184,20 @@ class Net:
         return logits, v
 
 
+def c_expf(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros_like(x)
+    lib().orc_expf(_p(x), C.c_int64(x.size), _p(y))
+    return y
+
+
+def sigmoid(x: np.ndarray) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros_like(x)
+    lib().orc_sigmoid(_p(x), C.c_int64(x.size), _p(y))
+    return y
+
+
 def softmax(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32).copy()
     lib().orc_softmax(_p(x), x.shape[1], C.c_int64(x.shape[0]))

@@ -485,8 +485,28 @@ static inline float bf16_round(float x) {  // round-to-nearest-even to bfloat16,
   float r; memcpy(&r, &u, 4); return r;
 }
 static inline float relu(float x) { return x > 0.f ? x : 0.f; }
+
+// exp as SPECIFIED for this path (DESIGN.md "canonical exp"): the reference takes exp from the platform
+// (NNlib softmax!/σ -> CUDA libdevice / Julia Base), which is not reproducible across CPU and GPU, so the
+// oracle and the kernels both evaluate this fixed sequence of exactly-rounded fp32 operations:
+// Cody–Waite reduction x = k ln2 + r, degree-7 Taylor/Horner for e^r, scale by 2^k.  <= 2 ulp from exp.
+static inline float c_expf(float x) {
+  if (x < -87.0f) return 0.0f;
+  if (x > 88.0f) x = 88.0f;
+  const float log2e = 1.44269504088896341f, ln2_hi = 0.693145751953125f, ln2_lo = 1.42860682030941723212e-6f;
+  float t = x * log2e;
+  float kf = (t + 12582912.0f) - 12582912.0f;     // nearest integer (ties to even), exact for |t| < 2^22
+  float r = (x - kf * ln2_hi) - kf * ln2_lo;
+  const float c[8] = {1.9841269841e-4f, 1.3888888889e-3f, 8.3333333333e-3f, 4.1666666667e-2f, 1.6666666667e-1f, 0.5f, 1.0f, 1.0f};
+  float p = c[0];
+  for (int i = 1; i < 8; i++) p = p * r + c[i];    // compiled with -ffp-contract=off: mul then add, two roundings
+  int k = (int)kf;
+  uint32_t bits = (uint32_t)(k + 127) << 23;
+  float scale; memcpy(&scale, &bits, 4);
+  return p * scale;
+}
 // NNlib sigmoid, numerically stable form
-static inline float sigmoidf(float x) { float t = expf(-fabsf(x)); return x >= 0.f ? 1.f / (1.f + t) : t / (1.f + t); }
+static inline float sigmoidf(float x) { float t = c_expf(-fabsf(x)); return x >= 0.f ? 1.f / (1.f + t) : t / (1.f + t); }
 
 // mode 0: fp32 as the reference.  mode 1: "bf16-faithful" — weights and every MMA
 // operand rounded to bf16, fp32 accumulate, fp32 residual stream (what the
@@ -534,7 +554,7 @@ static void softmax_inplace(float* x, int A) {
   float m = x[0];
   for (int a = 1; a < A; a++) m = std::max(m, x[a]);
   float ssum = 0.f;
-  for (int a = 0; a < A; a++) { x[a] = expf(x[a] - m); ssum += x[a]; }
+  for (int a = 0; a < A; a++) { x[a] = c_expf(x[a] - m); ssum += x[a]; }
   for (int a = 0; a < A; a++) x[a] = x[a] / ssum;
 }
 
@@ -955,6 +975,8 @@ int orc_net_forward(void* netp, const float* x, int64_t L, float* logits, float*
   }
   return 0;
 }
+void orc_expf(const float* x, int64_t n, float* y) { for (int64_t i = 0; i < n; i++) y[i] = c_expf(x[i]); }
+void orc_sigmoid(const float* x, int64_t n, float* y) { for (int64_t i = 0; i < n; i++) y[i] = sigmoidf(x[i]); }
 void orc_softmax(float* x, int A, int64_t L) { for (int64_t i = 0; i < L; i++) softmax_inplace(x + (size_t)A * i, A); }
 
 // ---- tree / search ----
