@@ -1,9 +1,365 @@
-// nn_tc.cu — placeholder until the tcgen05 chain lands (next commit): reports "unsupported" so that
-// AGPU_NN_BF16_TC contexts fail loudly instead of silently using another evaluator.
+// nn_tc.cu — snetwork2 forward (DenseNet.jl:294-304) as a bf16 tcgen05/TMEM GEMM chain for sm_100a.
+//
+// One CTA evaluates 256 leaf positions (two M=128 tiles) through ALL layers without touching HBM in
+// between:  x -> relu(W0 x) -> k x [ b = relu(b + relu(W b)) ] -> (policy | value) heads.
+//
+//   warps 0-3  : tile 0   } each warpgroup owns one 128-row tile: builds the A operand (0/1 encoding of the
+//   warps 4-7  : tile 1   } leaf bitboards, straight from the tree record), one elected lane issues the
+//                           tcgen05.mma chain of the layer, all 128 threads run the epilogue (tcgen05.ld of
+//                           their TMEM lane, residual/relu in fp32 registers, bf16 repack into the swizzled A
+//                           operand of the next layer).  While one warpgroup is in its epilogue the tensor
+//                           pipe runs the other tile's MMAs.
+//   warp 8     : weight producer — streams the per-layer weight images global->shared with 1-D bulk copies
+//                (cp.async.bulk, mbarrier complete_tx) through a 3-stage ring shared by both tiles.
+//
+// Operands: A (activations) and B (weights) are K-major bf16 with the 128-byte swizzle the UMMA shared-memory
+// descriptor expects (8-row x 128 B atoms, SBO = 1024 B); weights are pre-swizzled on the host into exactly
+// that image (tc_build_image), so a plain bulk copy lands them ready for the MMA.  Accumulators: fp32 in TMEM,
+// 128 columns per tile.  The residual stream stays in fp32 registers (one row per thread); only the MMA operand
+// is rounded to bf16 — the CPU oracle's "bf16-faithful" mode mirrors exactly these roundings.
+#include <cuda_bf16.h>
+
+#include <cstring>
+#include <vector>
+
 #include "nn.cuh"
+
 namespace ag {
-int tc_supported(int, int, int, int) { return 0; }
-size_t tc_image_bytes(int, int, int, int) { return 0; }
-void tc_build_image(const float*, const float* const*, const float*, const float*, const float*, const float*, int, int, int, int, void*, float*) {}
-cudaError_t tc_forward(const NetDev&, const NNInput&, int, float*, int, cudaStream_t) { return cudaErrorNotSupported; }
+
+namespace {
+
+constexpr int TC_N = 128;              // MLP width handled by this kernel
+constexpr int TC_TILE_M = 128;         // rows (games) per tile = UMMA M
+constexpr int TC_TILES = 2;            // tiles per CTA
+constexpr int TC_STAGES = 3;           // weight ring depth
+constexpr int TC_W_STAGE_BYTES = TC_N * TC_N * 2;                    // 32 KB: one 128x128 bf16 layer image
+constexpr int TC_A_BYTES = TC_TILE_M * TC_N * 2;                     // 32 KB per tile
+constexpr int TC_KTILE_BYTES_A = TC_TILE_M * 128;                    // 16 KB: 128 rows x 64 bf16
+constexpr int TC_THREADS = 32 * (4 * TC_TILES + 1);                  // 288
+constexpr int TC_SMEM = TC_TILES * TC_A_BYTES + TC_STAGES * TC_W_STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
+
+__host__ __device__ inline int head_n(int A) { return (A + 1 + 15) / 16 * 16; }
+
+// ---------------- PTX wrappers ----------------
+AG_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+AG_D void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+AG_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+AG_D void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+AG_D void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+AG_D void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+AG_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+AG_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+AG_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+AG_D void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+AG_D void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+AG_D void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, single CTA
+AG_D void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+AG_D void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+AG_D void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+AG_D void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: start>>4 | LBO(16B units)=1 | SBO=1024B | version 1 | layout 2
+AG_D uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N
+AG_D uint32_t umma_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24); }
+
+AG_D uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+struct TcArgs {
+  const unsigned char* img;   // layer images, back to back
+  const float* bias;          // [NH] head biases
+  int nlayers;                // 1 + k + 1 (base, k residual blocks, heads)
+  int k0_steps;               // UMMA K-steps of the base layer = ceil(2VS/16)
+  int A;                      // actions
+  int NH;                     // head N (multiple of 16)
+  int in;                     // 2*VS
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNInput I, int L, float* __restrict__ out, int outs) {
+  extern __shared__ unsigned char smem_raw[];
+  // 1024-byte alignment for the 128B swizzle atoms
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;                                          // [2][32 KB]
+  unsigned char* sW = smem + TC_TILES * TC_A_BYTES;                  // [3][32 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + TC_STAGES * TC_W_STAGE_BYTES);
+  // bars[0..2] full, [3..5] empty, [6..7] mma_done, then the TMEM base word
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_TILES); }
+    for (int t = 0; t < TC_TILES; t++) mbar_init(bar_done + 8 * t, 1);
+    fence_barrier_init();
+  }
+  if (warp == 4 * TC_TILES) tmem_alloc(smem_u32(tmem_slot), 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4 * TC_TILES) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      size_t off = 0;
+      for (int l = 0; l < T.nlayers; l++) {
+        const int s = l % TC_STAGES;
+        const uint32_t bytes = (l == T.nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
+        if (l >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((l / TC_STAGES) - 1) & 1);
+        mbar_expect_tx(bar_full + 8 * s, bytes);
+        bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + off, bytes, bar_full + 8 * s);
+        off += bytes;
+      }
+    }
+  } else {
+    // ===================== tile warpgroups =====================
+    const int t = warp >> 2;                       // tile of this warpgroup
+    const int r = (warp & 3) * 32 + lane;          // row in tile == TMEM lane
+    const int g = blockIdx.x * (TC_TILES * TC_TILE_M) + t * TC_TILE_M + r;
+    unsigned char* At = sA + t * TC_A_BYTES;
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);                       // column offset of this tile
+    const uint32_t tmem_row = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);          // + lane base of this warp's subpartition
+
+    // ---- A operand of the base layer: 0/1 encoding of the leaf position (decoder, mcts_gpu.jl:202-223) ----
+    {
+      u64 b[6] = {0, 0, 0, 0, 0, 0};
+      const float* xd = nullptr;
+      if (g < L) {
+        if (I.x_direct) xd = I.x_direct + (size_t)g * (2 * I.VS);
+        else {
+          const u64* st = reinterpret_cast<const u64*>(I.tree + (size_t)g * I.game_stride + (size_t)I.leaf[g] * I.rec + I.off_state);
+          for (int c = 0; c < 2 * I.nc; c++) b[c] = st[c];
+        }
+      }
+      const int VS = I.VS, nc = I.nc;
+#pragma unroll 1
+      for (int c = 0; c < 16; c++) {               // 16 chunks of 8 bf16 = K 128
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          float f[2];
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int k = c * 8 + e * 2 + h;
+            float v = 0.f;
+            if (k < 2 * VS && g < L) {
+              if (xd) v = xd[k];
+              else {
+                const int kk = k < VS ? k : k - VS;
+                const int ci = (k < VS ? 0 : nc) + (kk >> 6);
+                v = ((b[ci] >> (kk & 63)) & 1) ? 1.f : 0.f;
+              }
+            }
+            f[h] = v;
+          }
+          w[e] = pack_bf16(f[0], f[1]);
+        }
+        const int ktile = c >> 3, cc = c & 7;
+        *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_proxy_async();
+    named_bar_sync(1 + t, 128);
+
+    float h[TC_N];                                   // fp32 residual stream of this row
+#pragma unroll
+    for (int i = 0; i < TC_N; i++) h[i] = 0.f;
+
+    for (int l = 0; l < T.nlayers; l++) {
+      const int s = l % TC_STAGES;
+      const bool is_head = (l == T.nlayers - 1);
+      const int nl = is_head ? T.NH : TC_N;
+      if ((warp & 3) == 0 && lane == 0) {
+        // ---- MMA issue: D[128 x nl] = A[128 x K] * W_l[nl x K]^T ----
+        mbar_wait(bar_full + 8 * s, (l / TC_STAGES) & 1);
+        tc_fence_after();
+        const int ksteps = (l == 0) ? T.k0_steps : TC_N / 16;
+        const uint32_t a0 = smem_u32(At), b0 = smem_u32(sW + s * TC_W_STAGE_BYTES);
+        const uint32_t idesc = umma_idesc(nl);
+        for (int ks = 0; ks < ksteps; ks++) {
+          const int ktile = ks >> 2, kin = ks & 3;
+          const uint64_t ad = umma_desc(a0 + ktile * TC_KTILE_BYTES_A + kin * 32);
+          const uint64_t bd = umma_desc(b0 + ktile * (nl * 128) + kin * 32);
+          umma_bf16(tmem_acc, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_done + 8 * t);               // accumulator ready -> epilogue of this tile
+        umma_commit(bar_empty + 8 * s);              // weight stage consumed by this tile
+      }
+      mbar_wait(bar_done + 8 * t, l & 1);
+      tc_fence_after();
+
+      if (!is_head) {
+        // ---- epilogue: b = relu(acc) (base) or relu(b + relu(acc)); next A operand = bf16(b) ----
+#pragma unroll
+        for (int cb = 0; cb < TC_N / 32; cb++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_row + cb * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const float acc = __uint_as_float(v[i]);
+            const float ra = fmaxf(acc, 0.f);
+            h[cb * 32 + i] = (l == 0) ? ra : fmaxf(h[cb * 32 + i] + ra, 0.f);
+          }
+#pragma unroll
+          for (int c4 = 0; c4 < 4; c4++) {           // 4 chunks of 8 columns
+            const int c = cb * 4 + c4;               // chunk index in the row, 0..15
+            const float* hh = &h[c * 8];
+            const uint4 pk = make_uint4(pack_bf16(hh[0], hh[1]), pack_bf16(hh[2], hh[3]), pack_bf16(hh[4], hh[5]), pack_bf16(hh[6], hh[7]));
+            const int ktile = c >> 3, cc = c & 7;
+            *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+          }
+        }
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1 + t, 128);
+      } else {
+        // ---- heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) ----
+        float* o = out + (size_t)g * outs;
+        for (int cb = 0; cb * 32 < T.NH; cb++) {
+          uint32_t v[32];
+          tmem_ld32(tmem_row + cb * 32, v);
+          tmem_ld_wait();
+          if (g < L) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) {
+              const int a = cb * 32 + i;
+              if (a <= T.A) {
+                const float z = __uint_as_float(v[i]) + T.bias[a];
+                o[a] = (a == T.A) ? c_sigmoidf(z) : z;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4 * TC_TILES) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+inline uint16_t f2bf(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7F800000u) != 0x7F800000u) u += 0x7FFFu + ((u >> 16) & 1u);
+  return (uint16_t)(u >> 16);
+}
+
+// image of one layer: W[n][k] (n < rows, k < kreal; zero elsewhere), K padded to 128, as two K-tiles of
+// [rows_pad x 64] bf16 with the 128B swizzle: chunk' = chunk ^ (n & 7)
+void put_layer(unsigned char* img, int rows_pad, int rows, int kreal, const std::vector<float>& w /* row-major [rows][kreal] */) {
+  memset(img, 0, (size_t)rows_pad * TC_N * 2);
+  for (int n = 0; n < rows; n++)
+    for (int k = 0; k < kreal; k++) {
+      const int ktile = k >> 6, kk = k & 63, chunk = kk >> 3;
+      const size_t off = (size_t)ktile * rows_pad * 128 + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
+      const uint16_t v = f2bf(w[(size_t)n * kreal + k]);
+      memcpy(img + off, &v, 2);
+    }
+}
+
+}  // namespace
+
+int tc_supported(int in, int n, int k, int A) { return n == TC_N && in <= TC_N && k >= 0 && head_n(A) <= TC_N; }
+
+size_t tc_image_bytes(int in, int n, int k, int A) {
+  (void)in;
+  return (size_t)(1 + k) * n * n * 2 + (size_t)head_n(A) * n * 2;
+}
+
+void tc_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
+                    const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host) {
+  unsigned char* img = (unsigned char*)img_host;
+  std::vector<float> w;
+  // base: Julia (n x in) column-major -> row-major [n][in]
+  w.assign((size_t)n * in, 0.f);
+  for (int o = 0; o < n; o++) for (int i = 0; i < in; i++) w[(size_t)o * in + i] = base[o + (size_t)n * i];
+  put_layer(img, n, n, in, w);
+  img += (size_t)n * n * 2;
+  for (int l = 0; l < k; l++) {
+    w.assign((size_t)n * n, 0.f);
+    for (int o = 0; o < n; o++) for (int i = 0; i < n; i++) w[(size_t)o * n + i] = res[l][o + (size_t)n * i];
+    put_layer(img, n, n, n, w);
+    img += (size_t)n * n * 2;
+  }
+  const int NH = head_n(A);
+  w.assign((size_t)(A + 1) * n, 0.f);
+  for (int a = 0; a < A; a++) for (int i = 0; i < n; i++) w[(size_t)a * n + i] = pol_w[a + (size_t)A * i];
+  for (int i = 0; i < n; i++) w[(size_t)A * n + i] = val_w[i];
+  put_layer(img, NH, A + 1, n, w);
+  for (int a = 0; a < 256; a++) bias_host[a] = 0.f;
+  for (int a = 0; a < A; a++) bias_host[a] = pol_b[a];
+  bias_host[A] = val_b[0];
+}
+
+cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_mlp128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  TcArgs T;
+  T.img = (const unsigned char*)net.tc_img; T.bias = net.tc_bias; T.nlayers = net.k + 2; T.k0_steps = (net.in + 15) / 16; T.A = net.A;
+  T.NH = head_n(net.A); T.in = net.in;
+  const int grid = (L + TC_TILES * TC_TILE_M - 1) / (TC_TILES * TC_TILE_M);
+  tc_mlp128_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(T, I, L, out, outs);
+  return cudaGetLastError();
+}
+
+}  // namespace ag
