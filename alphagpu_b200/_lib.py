@@ -9,11 +9,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libalphagpu.so")
+SO_PATH = os.environ.get("AGPU_LIB", os.path.join(HERE, "libalphagpu.so"))   # AGPU_LIB: development variants
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_ILLEGAL_MOVE = 0, -1, -2, -3, -4, -5
 CONNECT4, GOBANG, HEX, REVERSI8, REVERSI6 = 0, 1, 2, 3, 4
-NN_BF16_TC, NN_FP32 = 0, 1
+NN_BF16_TC, NN_FP32, NN_FP16_TC = 0, 1, 2
 NKERNELS = 8
 KERNEL_CLASSES = ("select", "nn", "expand_backup", "begin", "finish_ply", "compact", "finalize", "other")
 

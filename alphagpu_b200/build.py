@@ -46,6 +46,14 @@ def _compile(src, verbose):
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    global OBJ, SO
+    extra = os.environ.get("AGPU_EXTRA_NVCC", "")       # development: e.g. "-DAG_LANES_SHIFT=2" with AGPU_VARIANT=w2
+    variant = os.environ.get("AGPU_VARIANT", "")
+    if variant:
+        OBJ = os.path.join(HERE, "_obj_" + variant)
+        SO = os.path.join(HERE, f"libalphagpu_{variant}.so")
+    if extra:
+        FLAGS.extend(extra.split())
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):

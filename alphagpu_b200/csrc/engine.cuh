@@ -174,11 +174,11 @@ struct EngineT : EngineBase {
     AG_REQUIRE(cfg.rollouts >= 1 && cfg.rollouts <= 255, AGPU_ERR_INVALID, "rollouts must be in 1..255 (node ids are stored in 8 bits)");
     AG_REQUIRE(cfg.max_games >= 1 && cfg.max_games <= (1ll << 30), AGPU_ERR_INVALID, "max_games out of range");
     AG_REQUIRE(cfg.width >= 1 && cfg.width <= 1024 && cfg.width >= A + 1 && cfg.blocks >= 0 && cfg.blocks <= 64, AGPU_ERR_INVALID, "unsupported MLP shape");
-    AG_REQUIRE(cfg.nn_mode == AGPU_NN_FP32 || cfg.nn_mode == AGPU_NN_BF16_TC, AGPU_ERR_INVALID, "bad nn_mode");
+    AG_REQUIRE(cfg.nn_mode == AGPU_NN_FP32 || cfg.nn_mode == AGPU_NN_BF16_TC || cfg.nn_mode == AGPU_NN_FP16_TC, AGPU_ERR_INVALID, "bad nn_mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { err = "no CUDA device (there is no CPU fallback)"; return AGPU_ERR_NO_DEVICE; }
-    if (cfg.nn_mode == AGPU_NN_BF16_TC)
-      AG_REQUIRE(tc_supported(2 * G::VS, cfg.width, cfg.blocks, A), AGPU_ERR_INVALID, "bf16 tensor-core chain does not support this MLP shape (width must be 128 or 512 with 2*VS <= 256, A+1 <= 128)");
+    if (is_tc())
+      AG_REQUIRE(tc_supported(2 * G::VS, cfg.width, cfg.blocks, A), AGPU_ERR_INVALID, "the tensor-core chain does not support this MLP shape yet (width must be 128, 2*VS <= 128, A+1 <= 128)");
     AG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, AGPU_ERR_INVALID, "device ordinal out of range");
     AG_CK(cudaSetDevice(cfg.device));
     AG_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -201,6 +201,8 @@ struct EngineT : EngineBase {
     return AGPU_OK;
   }
 
+  bool is_tc() const { return cfg.nn_mode == AGPU_NN_BF16_TC || cfg.nn_mode == AGPU_NN_FP16_TC; }
+  int tc_fmt() const { return cfg.nn_mode == AGPU_NN_FP16_TC ? 1 : 0; }
   static int blocks_for_groups(int64_t L) { return (int)((L * Lay::W + 255) / 256); }
   static int blocks_for_threads(int64_t n) { return (int)((n + 255) / 256); }
 
@@ -232,11 +234,11 @@ struct EngineT : EngineBase {
     s.dev.in = in; s.dev.n = n; s.dev.k = k; s.dev.A = A;
     s.dev.base = s.base.p; s.dev.res = s.res.p; s.dev.pol_w = s.pol_w.p; s.dev.pol_b = s.pol_b.p; s.dev.val_w = s.val_w.p; s.dev.val_b = s.val_b.p;
     s.dev.tc_img = nullptr; s.dev.tc_bias = nullptr;
-    if (cfg.nn_mode == AGPU_NN_BF16_TC) {
+    if (is_tc()) {
       const size_t bytes = tc_image_bytes(in, n, k, A);
       std::vector<unsigned char> img(bytes);
       std::vector<float> bias(256, 0.f);
-      tc_build_image(base, res, pol_w, pol_b, val_w, val_b, in, n, k, A, img.data(), bias.data());
+      tc_build_image(base, res, pol_w, pol_b, val_w, val_b, in, n, k, A, img.data(), bias.data(), tc_fmt());
       AG_CK(s.tc_img.ensure(bytes)); AG_CK(s.tc_bias.ensure(256));
       AG_CK(cudaMemcpyAsync(s.tc_img.p, img.data(), bytes, cudaMemcpyHostToDevice, stream));
       AG_CK(cudaMemcpyAsync(s.tc_bias.p, bias.data(), 256 * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -250,9 +252,9 @@ struct EngineT : EngineBase {
 
   int run_nn(int slot, const NNInput& I, int64_t L, float* out, int outs) {
     const NetSlot& s = nets[slot];
-    if (cfg.nn_mode == AGPU_NN_BF16_TC) {
+    if (is_tc()) {
       cudaError_t e = cudaSuccess;
-      launch(K_NN, [&] { e = tc_forward(s.dev, I, (int)L, out, outs, stream); });
+      launch(K_NN, [&] { e = tc_forward(s.dev, I, (int)L, out, outs, stream, tc_fmt()); });
       AG_CK(e);
     } else {
       constexpr int GT = 8;

@@ -111,8 +111,9 @@ struct TcPlan;   // opaque per-network plan
 int tc_supported(int in, int n, int k, int A);
 size_t tc_image_bytes(int in, int n, int k, int A);
 // builds the bf16 swizzled operand images from the fp32 column-major weights (host side), returns bytes written
+// fmt: 0 = bf16 operands, 1 = fp16 operands (both kind::f16 MMAs with fp32 accumulation)
 void tc_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
-                    const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host);
-cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream);
+                    const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host, int fmt);
+cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt);
 
 }  // namespace ag

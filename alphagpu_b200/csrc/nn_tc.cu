@@ -9,8 +9,10 @@
 //                           their TMEM lane, residual/relu in fp32 registers, bf16 repack into the swizzled A
 //                           operand of the next layer).  While one warpgroup is in its epilogue the tensor
 //                           pipe runs the other tile's MMAs.
-//   warp 8     : weight producer — streams the per-layer weight images global->shared with 1-D bulk copies
-//                (cp.async.bulk, mbarrier complete_tx) through a 3-stage ring shared by both tiles.
+//   weight producer: the issuing lane of tile 0 also streams the per-layer weight images global->shared with 1-D
+//                bulk copies (cp.async.bulk, mbarrier complete_tx) through a 3-stage ring shared by both tiles, two
+//                layers ahead of the MMAs.  (No ninth warp: with 9 warps one SM sub-partition hosts 3 of them and
+//                the register budget drops from 255 to 168 per thread, which spills the fp32 residual row.)
 //
 // Operands: A (activations) and B (weights) are K-major bf16 with the 128-byte swizzle the UMMA shared-memory
 // descriptor expects (8-row x 128 B atoms, SBO = 1024 B); weights are pre-swizzled on the host into exactly
@@ -35,7 +37,7 @@ constexpr int TC_STAGES = 3;           // weight ring depth
 constexpr int TC_W_STAGE_BYTES = TC_N * TC_N * 2;                    // 32 KB: one 128x128 bf16 layer image
 constexpr int TC_A_BYTES = TC_TILE_M * TC_N * 2;                     // 32 KB per tile
 constexpr int TC_KTILE_BYTES_A = TC_TILE_M * 128;                    // 16 KB: 128 rows x 64 bf16
-constexpr int TC_THREADS = 32 * (4 * TC_TILES + 1);                  // 288
+constexpr int TC_THREADS = 32 * 4 * TC_TILES;                        // 256: 2 warps per SM sub-partition, so up to 255 registers per thread
 constexpr int TC_SMEM = TC_TILES * TC_A_BYTES + TC_STAGES * TC_W_STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
 
 __host__ __device__ inline int head_n(int A) { return (A + 1 + 15) / 16 * 16; }
@@ -89,6 +91,15 @@ AG_D void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id
 AG_D void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+AG_D void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 AG_D void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -108,11 +119,19 @@ AG_D uint64_t umma_desc(uint32_t saddr) {
   return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor: D fp32, A/B bf16, both K-major, M=128, N
-AG_D uint32_t umma_idesc(int n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24); }
+// (a_format/b_format: 0 = F16, 1 = BF16)
+template <int FMT> AG_D uint32_t umma_idesc(int n) {
+  const uint32_t f = (FMT == 0) ? 1u : 0u;
+  return (1u << 4) | (f << 7) | (f << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TC_TILE_M >> 4) << 24);
+}
 
-AG_D uint32_t pack_bf16(float lo, float hi) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&t);
+// two fp32 -> one packed pair of MMA operands (element `lo` in the low half).  FMT 0: bf16 (RNE).  FMT 1: fp16 (RNE, saturating
+// to +-65504 so that an outlier activation cannot become inf)
+template <int FMT> AG_D uint32_t pack2(float lo, float hi) {
+  uint32_t d;
+  if (FMT == 0) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 
 struct TcArgs {
@@ -125,6 +144,7 @@ struct TcArgs {
   int in;                     // 2*VS
 };
 
+template <int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNInput I, int L, float* __restrict__ out, int outs) {
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
@@ -143,26 +163,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
     for (int t = 0; t < TC_TILES; t++) mbar_init(bar_done + 8 * t, 1);
     fence_barrier_init();
   }
-  if (warp == 4 * TC_TILES) tmem_alloc(smem_u32(tmem_slot), 256);
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4 * TC_TILES) {
-    // ===================== weight producer =====================
-    if (lane == 0) {
-      size_t off = 0;
-      for (int l = 0; l < T.nlayers; l++) {
-        const int s = l % TC_STAGES;
-        const uint32_t bytes = (l == T.nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
-        if (l >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((l / TC_STAGES) - 1) & 1);
-        mbar_expect_tx(bar_full + 8 * s, bytes);
-        bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + off, bytes, bar_full + 8 * s);
-        off += bytes;
-      }
-    }
-  } else {
+  // weight image of layer l -> ring stage l % 3 (called by one thread)
+  auto load_layer = [&](int l) {
+    const int s = l % TC_STAGES;
+    const uint32_t bytes = (l == T.nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
+    if (l >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((l / TC_STAGES) - 1) & 1);    // both tiles' MMAs of layer l-3 have drained
+    mbar_expect_tx(bar_full + 8 * s, bytes);
+    bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + (size_t)l * TC_W_STAGE_BYTES, bytes, bar_full + 8 * s);
+  };
+  if (threadIdx.x == 0) {
+    load_layer(0);
+    if (T.nlayers > 1) load_layer(1);
+  }
+  {
     // ===================== tile warpgroups =====================
     const int t = warp >> 2;                       // tile of this warpgroup
     const int r = (warp & 3) * 32 + lane;          // row in tile == TMEM lane
@@ -173,15 +192,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
 
     // ---- A operand of the base layer: 0/1 encoding of the leaf position (decoder, mcts_gpu.jl:202-223) ----
     {
-      u64 b[6] = {0, 0, 0, 0, 0, 0};
+      u64 b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
       const float* xd = nullptr;
       if (g < L) {
         if (I.x_direct) xd = I.x_direct + (size_t)g * (2 * I.VS);
         else {
           const u64* st = reinterpret_cast<const u64*>(I.tree + (size_t)g * I.game_stride + (size_t)I.leaf[g] * I.rec + I.off_state);
-          for (int c = 0; c < 2 * I.nc; c++) b[c] = st[c];
+          const int nch = 2 * I.nc;
+          b0 = st[0]; b1 = st[1];
+          if (nch > 2) { b2 = st[2]; b3 = st[3]; }
+          if (nch > 4) { b4 = st[4]; b5 = st[5]; }
         }
       }
+      auto getb = [&](int ci) -> u64 { return ci == 0 ? b0 : ci == 1 ? b1 : ci == 2 ? b2 : ci == 3 ? b3 : ci == 4 ? b4 : b5; };
       const int VS = I.VS, nc = I.nc;
 #pragma unroll 1
       for (int c = 0; c < 16; c++) {               // 16 chunks of 8 bf16 = K 128
@@ -198,12 +221,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
               else {
                 const int kk = k < VS ? k : k - VS;
                 const int ci = (k < VS ? 0 : nc) + (kk >> 6);
-                v = ((b[ci] >> (kk & 63)) & 1) ? 1.f : 0.f;
+                v = ((getb(ci) >> (kk & 63)) & 1) ? 1.f : 0.f;
               }
             }
             f[h] = v;
           }
-          w[e] = pack_bf16(f[0], f[1]);
+          w[e] = pack2<FMT>(f[0], f[1]);
         }
         const int ktile = c >> 3, cc = c & 7;
         *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -226,7 +249,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
         tc_fence_after();
         const int ksteps = (l == 0) ? T.k0_steps : TC_N / 16;
         const uint32_t a0 = smem_u32(At), b0 = smem_u32(sW + s * TC_W_STAGE_BYTES);
-        const uint32_t idesc = umma_idesc(nl);
+        const uint32_t idesc = umma_idesc<FMT>(nl);
         for (int ks = 0; ks < ksteps; ks++) {
           const int ktile = ks >> 2, kin = ks & 3;
           const uint64_t ad = umma_desc(a0 + ktile * TC_KTILE_BYTES_A + kin * 32);
@@ -235,31 +258,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
         }
         umma_commit(bar_done + 8 * t);               // accumulator ready -> epilogue of this tile
         umma_commit(bar_empty + 8 * s);              // weight stage consumed by this tile
+        if (t == 0 && l + 2 < T.nlayers) load_layer(l + 2);   // producer role: keep the ring two layers ahead
       }
       mbar_wait(bar_done + 8 * t, l & 1);
       tc_fence_after();
 
       if (!is_head) {
-        // ---- epilogue: b = relu(acc) (base) or relu(b + relu(acc)); next A operand = bf16(b) ----
+        // ---- epilogue: b = relu(acc) (base) or relu(b + relu(acc)); next A operand = bf16/fp16(b) ----
+        uint32_t va[16], vb[16];
+        auto process = [&](const int cb, const uint32_t (&cur)[16]) {      // columns 16*cb .. 16*cb+15
 #pragma unroll
-        for (int cb = 0; cb < TC_N / 32; cb++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_row + cb * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const float acc = __uint_as_float(v[i]);
-            const float ra = fmaxf(acc, 0.f);
-            h[cb * 32 + i] = (l == 0) ? ra : fmaxf(h[cb * 32 + i] + ra, 0.f);
+          for (int i = 0; i < 16; i++) {
+            const float ra = fmaxf(__uint_as_float(cur[i]), 0.f);
+            h[cb * 16 + i] = (l == 0) ? ra : fmaxf(h[cb * 16 + i] + ra, 0.f);
           }
 #pragma unroll
-          for (int c4 = 0; c4 < 4; c4++) {           // 4 chunks of 8 columns
-            const int c = cb * 4 + c4;               // chunk index in the row, 0..15
-            const float* hh = &h[c * 8];
-            const uint4 pk = make_uint4(pack_bf16(hh[0], hh[1]), pack_bf16(hh[2], hh[3]), pack_bf16(hh[4], hh[5]), pack_bf16(hh[6], hh[7]));
+          for (int c2 = 0; c2 < 2; c2++) {           // 2 chunks of 8 columns
+            const int c = cb * 2 + c2;               // chunk index in the row, 0..15
+            const uint4 pk = make_uint4(pack2<FMT>(h[c * 8 + 0], h[c * 8 + 1]), pack2<FMT>(h[c * 8 + 2], h[c * 8 + 3]),
+                                        pack2<FMT>(h[c * 8 + 4], h[c * 8 + 5]), pack2<FMT>(h[c * 8 + 6], h[c * 8 + 7]));
             const int ktile = c >> 3, cc = c & 7;
             *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
           }
+        };
+        // the TMEM load of the next 16 columns is in flight while the current ones are processed
+        tmem_ld16(tmem_row, va);
+#pragma unroll
+        for (int cb = 0; cb < TC_N / 16; cb += 2) {
+          tmem_ld_wait();
+          tmem_ld16(tmem_row + (cb + 1) * 16, vb);
+          process(cb, va);
+          tmem_ld_wait();
+          if (cb + 2 < TC_N / 16) tmem_ld16(tmem_row + (cb + 2) * 16, va);
+          process(cb + 1, vb);
         }
         tc_fence_before();
         fence_proxy_async();
@@ -287,7 +318,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
     }
   }
   __syncthreads();
-  if (warp == 4 * TC_TILES) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
@@ -299,16 +330,37 @@ inline uint16_t f2bf(float f) {
   if ((u & 0x7F800000u) != 0x7F800000u) u += 0x7FFFu + ((u >> 16) & 1u);
   return (uint16_t)(u >> 16);
 }
+// fp32 -> fp16, round to nearest even, saturating to +-65504 (matches cvt.rn.satfinite.f16.f32)
+inline uint16_t f2h(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  const uint16_t sign = (uint16_t)((u >> 16) & 0x8000u);
+  const uint32_t a = u & 0x7FFFFFFFu;
+  if (a >= 0x477FF000u) return sign | 0x7BFF;                 // >= 65520 (or inf/nan): saturate to 65504
+  if (a < 0x33000001u) return sign;                           // < 2^-25 (rounds to zero)
+  int e = (int)(a >> 23) - 127;
+  uint32_t m = (a & 0x7FFFFFu) | 0x800000u;
+  if (e < -14) {                                              // subnormal half
+    const int sh = 13 + (-14 - e);
+    uint32_t q = m >> sh, rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (q & 1u))) q++;
+    return sign | (uint16_t)q;
+  }
+  uint32_t q = m >> 13, rem = m & 0x1FFFu;
+  uint32_t h = ((uint32_t)(e + 15) << 10) + (q - 0x400u);
+  if (rem > 0x1000u || (rem == 0x1000u && (q & 1u))) h++;
+  return sign | (uint16_t)h;
+}
 
 // image of one layer: W[n][k] (n < rows, k < kreal; zero elsewhere), K padded to 128, as two K-tiles of
 // [rows_pad x 64] bf16 with the 128B swizzle: chunk' = chunk ^ (n & 7)
-void put_layer(unsigned char* img, int rows_pad, int rows, int kreal, const std::vector<float>& w /* row-major [rows][kreal] */) {
+void put_layer(unsigned char* img, int rows_pad, int rows, int kreal, const std::vector<float>& w /* row-major [rows][kreal] */, int fmt) {
   memset(img, 0, (size_t)rows_pad * TC_N * 2);
   for (int n = 0; n < rows; n++)
     for (int k = 0; k < kreal; k++) {
       const int ktile = k >> 6, kk = k & 63, chunk = kk >> 3;
       const size_t off = (size_t)ktile * rows_pad * 128 + (size_t)n * 128 + (size_t)((chunk ^ (n & 7)) << 4) + (size_t)(kk & 7) * 2;
-      const uint16_t v = f2bf(w[(size_t)n * kreal + k]);
+      const uint16_t v = fmt == 0 ? f2bf(w[(size_t)n * kreal + k]) : f2h(w[(size_t)n * kreal + k]);
       memcpy(img + off, &v, 2);
     }
 }
@@ -323,34 +375,35 @@ size_t tc_image_bytes(int in, int n, int k, int A) {
 }
 
 void tc_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
-                    const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host) {
+                    const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host, int fmt) {
   unsigned char* img = (unsigned char*)img_host;
   std::vector<float> w;
   // base: Julia (n x in) column-major -> row-major [n][in]
   w.assign((size_t)n * in, 0.f);
   for (int o = 0; o < n; o++) for (int i = 0; i < in; i++) w[(size_t)o * in + i] = base[o + (size_t)n * i];
-  put_layer(img, n, n, in, w);
+  put_layer(img, n, n, in, w, fmt);
   img += (size_t)n * n * 2;
   for (int l = 0; l < k; l++) {
     w.assign((size_t)n * n, 0.f);
     for (int o = 0; o < n; o++) for (int i = 0; i < n; i++) w[(size_t)o * n + i] = res[l][o + (size_t)n * i];
-    put_layer(img, n, n, n, w);
+    put_layer(img, n, n, n, w, fmt);
     img += (size_t)n * n * 2;
   }
   const int NH = head_n(A);
   w.assign((size_t)(A + 1) * n, 0.f);
   for (int a = 0; a < A; a++) for (int i = 0; i < n; i++) w[(size_t)a * n + i] = pol_w[a + (size_t)A * i];
   for (int i = 0; i < n; i++) w[(size_t)A * n + i] = val_w[i];
-  put_layer(img, NH, A + 1, n, w);
+  put_layer(img, NH, A + 1, n, w, fmt);
   for (int a = 0; a < 256; a++) bias_host[a] = 0.f;
   for (int a = 0; a < A; a++) bias_host[a] = pol_b[a];
   bias_host[A] = val_b[0];
 }
 
-cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream) {
+cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt) {
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_mlp128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(tc_mlp128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
@@ -358,7 +411,8 @@ cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, i
   T.img = (const unsigned char*)net.tc_img; T.bias = net.tc_bias; T.nlayers = net.k + 2; T.k0_steps = (net.in + 15) / 16; T.A = net.A;
   T.NH = head_n(net.A); T.in = net.in;
   const int grid = (L + TC_TILES * TC_TILE_M - 1) / (TC_TILES * TC_TILE_M);
-  tc_mlp128_kernel<<<grid, TC_THREADS, TC_SMEM, stream>>>(T, I, L, out, outs);
+  if (fmt == 0) tc_mlp128_kernel<0><<<grid, TC_THREADS, TC_SMEM, stream>>>(T, I, L, out, outs);
+  else tc_mlp128_kernel<1><<<grid, TC_THREADS, TC_SMEM, stream>>>(T, I, L, out, outs);
   return cudaGetLastError();
 }
 

@@ -35,12 +35,19 @@ static_assert(sizeof(NodeHdr) == 8, "header");
 
 constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+// Lanes cooperating on one game: W = pow2ceil(A) capped at a warp.  Measured on B200 (profiles/r01_lanes_sweep.txt,
+// Connect4): 8 lanes 64.6 us per select launch, 4 lanes 72.7, 2 lanes 96.5, 1 lane 138.8 — the descent is a serial
+// dependency chain per game, so spreading a node's actions over more lanes shortens it.  AG_LANES_SHIFT halves W per step.
+#ifndef AG_LANES_SHIFT
+#define AG_LANES_SHIFT 0
+#endif
 template <class G>
 struct Layout {
   static constexpr int A = G::A;
-  static constexpr int W = pow2ceil(A) < 32 ? pow2ceil(A) : 32;   // lanes per game
+  static constexpr int W0 = pow2ceil(A) < 32 ? pow2ceil(A) : 32;
+  static constexpr int W = (A <= 32 && (W0 >> AG_LANES_SHIFT) >= 1) ? (W0 >> AG_LANES_SHIFT) : W0;   // lanes per game
   static constexpr int APL = (A + W - 1) / W;                      // actions per lane
-  static constexpr int APAD = W * APL;
+  static constexpr int APAD = (W * APL + 7) / 8 * 8;
   static constexpr int GPW = 32 / W;                               // games per warp
   static constexpr int OFF_PRIOR = 0;
   static constexpr int OFF_Q = 4 * APAD;

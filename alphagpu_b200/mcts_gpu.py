@@ -48,7 +48,7 @@ class PoolSample:
 class Context:
     """One `init(positions, visits)` (mcts_gpu.jl:350-357): the tree arrays for `ngames` games × `visits` nodes on one GPU."""
 
-    def __init__(self, spec: GameSpec, visits: int, ngames: int, width: int, blocks: int, device: int = 0, nn_mode: int = _lib.NN_BF16_TC):
+    def __init__(self, spec: GameSpec, visits: int, ngames: int, width: int, blocks: int, device: int = 0, nn_mode: int = _lib.NN_FP16_TC):
         self.lib = _lib.load()
         self.spec, self.visits, self.ngames = spec, visits, ngames
         self.A, self.VS, self.FS = spec.maxActions, spec.VectorizedState, spec.FeatureSize
@@ -216,7 +216,7 @@ class Context:
 # ------------------------------------------------------------------------------------------------
 # The reference's public entry points
 # ------------------------------------------------------------------------------------------------
-def init(spec: GameSpec, visits: int, ngames: int, actor: SNetwork2, device: int = 0, nn_mode: int = _lib.NN_BF16_TC) -> Context:
+def init(spec: GameSpec, visits: int, ngames: int, actor: SNetwork2, device: int = 0, nn_mode: int = _lib.NN_FP16_TC) -> Context:
     """init(positions, visits) (mcts_gpu.jl:350-357) + the actor's weights made resident."""
     ctx = Context(spec, visits, ngames, actor.width, actor.blocks, device, nn_mode)
     ctx.set_weights(actor, 0)
@@ -224,7 +224,7 @@ def init(spec: GameSpec, visits: int, ngames: int, actor: SNetwork2, device: int
 
 
 def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample], *, spec: GameSpec, cpuct=2.0, noise=None, seed=0,
-         uid_base=0, device=0, nn_mode=_lib.NN_BF16_TC, ctx: Optional[Context] = None):
+         uid_base=0, device=0, nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
     """mcts(actor, visits, ngames, buffer; cpuct, noise) (mcts_gpu.jl:477-579): one generation of self-play; samples are
     pushed into `buffer`.  Returns (data, valid) like the reference plus the run statistics."""
     own = ctx is None
@@ -243,7 +243,7 @@ def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample
 
 
 def mcts_duel(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, cpuct=2.0, seed=0, device=0,
-              nn_mode=_lib.NN_BF16_TC, ctx: Optional[Context] = None):
+              nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
     """mcts(actor1, actor2, visits, ngames; cpuct) (mcts_gpu.jl:581-651) -> [v, n, d]."""
     own = ctx is None
     if own:
@@ -256,7 +256,7 @@ def mcts_duel(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *,
     return res
 
 
-def duelnetwork(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, seed=0, device=0, nn_mode=_lib.NN_BF16_TC):
+def duelnetwork(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, seed=0, device=0, nn_mode=_lib.NN_FP16_TC):
     """duelnetwork(actor1, actor2, visits, ngames) (mcts_gpu.jl:653-668): half the games with each net moving first."""
     h = ngames // 2
     v1, n1, d1 = mcts_duel(actor1, actor2, visits, h, spec=spec, seed=seed, device=device, nn_mode=nn_mode)

@@ -155,7 +155,7 @@ class Net:
     base (n, in), res[k] (n, n), policy (A, n), policy_bias (A,), value (1, n), value_bias (1,).
     Stored Fortran-ordered so the bytes equal Julia's column-major arrays."""
 
-    FP32, BF16, BF16_RESID = 0, 1, 2
+    FP32, BF16, BF16_RESID, F16 = 0, 1, 2, 3
 
     def __init__(self, base, res, policy, policy_bias, value, value_bias):
         f = lambda a: np.asfortranarray(np.asarray(a, dtype=np.float32))
@@ -195,6 +195,14 @@ def sigmoid(x: np.ndarray) -> np.ndarray:
     x = np.ascontiguousarray(x, dtype=np.float32)
     y = np.zeros_like(x)
     lib().orc_sigmoid(_p(x), C.c_int64(x.size), _p(y))
+    return y
+
+
+def round_to(x: np.ndarray, fmt: str) -> np.ndarray:
+    """round fp32 values to bf16 ('bf16') or saturating fp16 ('f16'), returned as fp32"""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.zeros_like(x)
+    lib().orc_round(_p(x), C.c_int64(x.size), _p(y), 1 if fmt == "f16" else 0)
     return y
 
 

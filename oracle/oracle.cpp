@@ -476,6 +476,9 @@ struct Net {
   // bf16-rounded copies of the matrices (modes 1, 2)
   std::vector<float> base_r, policy_r, value_r;
   std::vector<std::vector<float>> res_r;
+  // fp16-rounded copies (mode 3)
+  std::vector<float> base_h, policy_h, value_h;
+  std::vector<std::vector<float>> res_h;
 };
 
 static inline float bf16_round(float x) {  // round-to-nearest-even to bfloat16, back to fp32
@@ -483,6 +486,24 @@ static inline float bf16_round(float x) {  // round-to-nearest-even to bfloat16,
   if ((u & 0x7F800000u) == 0x7F800000u) return x;
   u += 0x7FFFu + ((u >> 16) & 1u); u &= 0xFFFF0000u;
   float r; memcpy(&r, &u, 4); return r;
+}
+// round-to-nearest-even to IEEE binary16, saturating to +-65504 (PTX cvt.rn.satfinite.f16.f32), back to fp32
+static inline float f16_round(float x) {
+  uint32_t u; memcpy(&u, &x, 4);
+  uint32_t sign = u & 0x80000000u, a = u & 0x7FFFFFFFu;
+  float r;
+  if (a >= 0x477FF000u) { r = 65504.0f; }                       // >= 65520: saturate
+  else if (a < 0x33000001u) { r = 0.0f; }                       // <= 2^-25: rounds to zero
+  else {
+    int e = (int)(a >> 23) - 127;
+    int drop = e < -14 ? 13 + (-14 - e) : 13;                   // mantissa bits that do not fit (more for subnormal halves)
+    uint32_t m = (a & 0x7FFFFFu) | 0x800000u;
+    uint32_t q = m >> drop, rem = m & ((1u << drop) - 1u), half = 1u << (drop - 1);
+    if (rem > half || (rem == half && (q & 1u))) q++;
+    r = ldexpf((float)q, e - 23 + drop);
+  }
+  uint32_t ru; memcpy(&ru, &r, 4); ru |= sign; memcpy(&r, &ru, 4);
+  return r;
 }
 static inline float relu(float x) { return x > 0.f ? x : 0.f; }
 
@@ -512,11 +533,13 @@ static inline float sigmoidf(float x) { float t = c_expf(-fabsf(x)); return x >=
 // operand rounded to bf16, fp32 accumulate, fp32 residual stream (what the
 // tcgen05 chain computes, up to accumulation order).
 // mode 2: as mode 1 but the residual stream itself is stored in bf16 (wide nets).
+// mode 3: as mode 1 with fp16 operands (saturating) instead of bf16.
 static void net_forward_one(const Net& net, const float* x, float* logits, float* v, int mode, float* b, float* t, float* op) {
   const int n = net.n;
-  const std::vector<float>& Wbase = mode ? net.base_r : net.base;
-  const std::vector<float>& Wpol = mode ? net.policy_r : net.policy;
-  const std::vector<float>& Wval = mode ? net.value_r : net.value;
+  const std::vector<float>& Wbase = mode == 3 ? net.base_h : mode ? net.base_r : net.base;
+  const std::vector<float>& Wpol = mode == 3 ? net.policy_h : mode ? net.policy_r : net.policy;
+  const std::vector<float>& Wval = mode == 3 ? net.value_h : mode ? net.value_r : net.value;
+  auto rnd = [mode](float v) { return mode == 3 ? f16_round(v) : mode ? bf16_round(v) : v; };
   // b = relu.(base * x)        DenseNet.jl:295
   for (int o = 0; o < n; o++) t[o] = 0.f;
   for (int i = 0; i < net.in; i++) {
@@ -528,8 +551,8 @@ static void net_forward_one(const Net& net, const float* x, float* logits, float
   if (mode == 2) for (int o = 0; o < n; o++) b[o] = bf16_round(b[o]);
   // for w in res: b .= relu.(b .+ relu.(w*b))   DenseNet.jl:297-299
   for (int l = 0; l < net.k; l++) {
-    const std::vector<float>& w = mode ? net.res_r[l] : net.res[l];
-    for (int o = 0; o < n; o++) { t[o] = 0.f; op[o] = mode ? bf16_round(b[o]) : b[o]; }
+    const std::vector<float>& w = mode == 3 ? net.res_h[l] : mode ? net.res_r[l] : net.res[l];
+    for (int o = 0; o < n; o++) { t[o] = 0.f; op[o] = rnd(b[o]); }
     for (int i = 0; i < n; i++) {
       float bi = op[i];
       for (int o = 0; o < n; o++) t[o] += w[o + n * i] * bi;
@@ -538,7 +561,7 @@ static void net_forward_one(const Net& net, const float* x, float* logits, float
     if (mode == 2) for (int o = 0; o < n; o++) b[o] = bf16_round(b[o]);
   }
   // policy*b .+ policy_bias , σ.(value*b .+ value_bias)     DenseNet.jl:301
-  for (int o = 0; o < n; o++) op[o] = mode ? bf16_round(b[o]) : b[o];
+  for (int o = 0; o < n; o++) op[o] = rnd(b[o]);
   for (int a = 0; a < net.A; a++) {
     float acc = 0.f;
     for (int i = 0; i < n; i++) acc += Wpol[a + net.A * i] * op[i];
@@ -958,6 +981,9 @@ void* orc_net_create(int in, int n, int k, int A, const float* base, const float
   auto rr = [](const std::vector<float>& w) { std::vector<float> r(w.size()); for (size_t i = 0; i < w.size(); i++) r[i] = bf16_round(w[i]); return r; };
   net->base_r = rr(net->base); net->policy_r = rr(net->policy); net->value_r = rr(net->value);
   for (int l = 0; l < k; l++) net->res_r.push_back(rr(net->res[l]));
+  auto rh = [](const std::vector<float>& w) { std::vector<float> r(w.size()); for (size_t i = 0; i < w.size(); i++) r[i] = f16_round(w[i]); return r; };
+  net->base_h = rh(net->base); net->policy_h = rh(net->policy); net->value_h = rh(net->value);
+  for (int l = 0; l < k; l++) net->res_h.push_back(rh(net->res[l]));
   return net;
 }
 void orc_net_destroy(void* net) { delete (Net*)net; }
@@ -977,6 +1003,7 @@ int orc_net_forward(void* netp, const float* x, int64_t L, float* logits, float*
 }
 void orc_expf(const float* x, int64_t n, float* y) { for (int64_t i = 0; i < n; i++) y[i] = c_expf(x[i]); }
 void orc_sigmoid(const float* x, int64_t n, float* y) { for (int64_t i = 0; i < n; i++) y[i] = sigmoidf(x[i]); }
+void orc_round(const float* x, int64_t n, float* y, int fmt) { for (int64_t i = 0; i < n; i++) y[i] = fmt == 1 ? f16_round(x[i]) : bf16_round(x[i]); }
 void orc_softmax(float* x, int A, int64_t L) { for (int64_t i = 0; i < L; i++) softmax_inplace(x + (size_t)A * i, A); }
 
 // ---- tree / search ----

@@ -17,7 +17,7 @@ ap.add_argument("--games", type=int, default=32768)
 ap.add_argument("--rollout", type=int, default=64)
 ap.add_argument("--width", type=int, default=128)
 ap.add_argument("--blocks", type=int, default=6)
-ap.add_argument("--nn-mode", type=int, default=0)
+ap.add_argument("--nn-mode", type=int, default=2)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--profile", type=int, default=1)
 a = ap.parse_args()
