@@ -165,17 +165,19 @@ class Context:
         return d
 
     # ---- whole loops ----
-    def selfplay(self, visits: int, ngames: int, *, cpuct=2.0, noise=0.0, seed=0, uid_base=0, slot=0, want_samples=True):
+    def selfplay(self, visits: int, ngames: int, *, cpuct=2.0, noise=0.0, seed=0, uid_base=0, slot=0, want_samples=True, out=None):
+        """agpu_selfplay.  `out`: optional preallocated (e.g. pinned) sample arrays keyed state/policy/player/value/fstate/game/ply."""
         res = np.zeros(3, np.int64)
         st = _lib.RunStats()
-        out = None
-        if want_samples:
-            cap = ngames * self.spec.maxLengthGame
-            out = dict(state=np.zeros((cap, 2 * self.VS), np.int8), policy=np.zeros((cap, self.A), np.float32), player=np.zeros(cap, np.int8),
-                       value=np.zeros(cap, np.float32), fstate=np.zeros((cap, self.FS), np.int8), game=np.zeros(cap, np.int32), ply=np.zeros(cap, np.int32))
+        if want_samples or out is not None:
+            if out is None:
+                cap = ngames * self.spec.maxLengthGame
+                out = dict(state=np.empty((cap, 2 * self.VS), np.int8), policy=np.empty((cap, self.A), np.float32), player=np.empty(cap, np.int8),
+                           value=np.empty(cap, np.float32), fstate=np.empty((cap, self.FS), np.int8), game=np.empty(cap, np.int32), ply=np.empty(cap, np.int32))
+            cap = out["player"].shape[0]
             sc = _lib.Samples(cap, 0, *[out[k].ctypes.data for k in ("state", "policy", "player", "value", "fstate", "game", "ply")])
             rc = self.lib.agpu_selfplay(self.h, slot, visits, ngames, uid_base, cpuct, noise, seed, C.byref(sc), _p(res), C.byref(st))
-            n = int(sc.count)
+            n = min(int(sc.count), cap)
             out = {k: v[:n] for k, v in out.items()}
         else:
             rc = self.lib.agpu_selfplay(self.h, slot, visits, ngames, uid_base, cpuct, noise, seed, None, _p(res), C.byref(st))

@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py — self-play MCTS sims/sec on BASELINE.json config 2 (Connect4, DenseNet 128x6, 64 rollouts, 32768 games per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One step = one self-play generation: `mcts(actor, 64, 32768, buffer)` played to the end of every game (mcts_gpu.jl:477-579).
+Each rank owns one GPU and an independent shard of games (uids rank*32768 ...): no collective on the search path, weak scaling.
+`value` is timed on the device (CUDA events on the library's stream, max over ranks) with weights and trees resident in HBM;
+`e2e` is the same metric through the public Python/C-ABI call with host buffers: weights copied host->device and all samples
+copied device->host inside the timed region.  `--impl reference` times the reference's CPU path (the C++ oracle port, OpenMP
+over games, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GAMES, ROLLOUT, WIDTH, BLOCKS, CPUCT = 32768, 64, 128, 6, 1.5
+WORKLOAD = "connect4_densenet128x6_rollout64_games32768"
+METRIC = "selfplay_mcts_sims_per_sec"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "measured"
+    except Exception:
+        return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 9 for i in range(4) if r[5 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def algorithmic_bytes_per_sim(A, S, dbar):
+    """SURVEY.md §8(d) / BASELINE.md §3, split by kernel.  A actions, S packed state bytes, dbar expanded nodes per descent."""
+    b_node = 12 * A + 2 * A + 8
+    select = dbar * b_node + (2 * S + 8 + 10 * A) + 4          # traversed nodes + child allocation (state r/w, header, zero-init) + leaf id
+    expand = 4 * A + 4 * (A + 1) + 16 * dbar + 4               # prior write, logits+value read, q/visits RMW per ancestor, leaf id
+    nn = S + 4 * (A + 1) + 4                                   # packed leaf state read, logits+value write, leaf id
+    return {"select": select, "expand_backup": expand, "nn": nn}
+
+
+def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port of mcts_gpu.jl, all host threads), bounded sample per step."""
+    if rank != 0:
+        return
+    import oracle
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import alphagpu_b200 as ag
+    spec = oracle.Spec(oracle.CONNECT4)
+    p = ag.ressimplesf(2 * spec.VS, spec.A, WIDTH, BLOCKS, seed=0)
+    net = oracle.Net(p.base, p.res, p.policy, p.policy_bias, p.value, p.value_bias)
+    sample_games = 256
+    times, sims = [], 0
+    for i in range(args.warmup + args.steps):
+        t = time.perf_counter()
+        res, st = oracle.selfplay(spec, net, ROLLOUT, sample_games, cpuct=CPUCT, seed=i)
+        dt = time.perf_counter() - t
+        if i >= args.warmup:
+            times.append(dt)
+            sims += st["sims"]
+    total = sum(times)
+    v = sims / total
+    cores = oracle.num_threads()
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "sims/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "sample": f"{sample_games} of {GAMES} games per step, played to the end"},
+            "cpu_baseline": {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x {sample_games} Connect4 games, 128x6 fp32 net, 64 rollouts, to completion ({sims} sims)"},
+            "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nn-mode", type=int, default=2, help="2 = fp16 tcgen05 chain (default), 0 = bf16 tcgen05 chain, 1 = fp32 CUDA cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import alphagpu_b200 as ag
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    spec = ag.GameSpec.named("connect4")
+    net = ag.ressimplesf(2 * spec.VectorizedState, spec.maxActions, WIDTH, BLOCKS, seed=0)
+    ctx = ag.Context(spec, ROLLOUT, GAMES, WIDTH, BLOCKS, device=local_rank, nn_mode=args.nn_mode)
+    ctx.set_weights(net)
+    uid_base = rank * GAMES
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up + device-resident timing (value) ----
+    for i in range(args.warmup):
+        ctx.selfplay(ROLLOUT, GAMES, cpuct=CPUCT, seed=1000 + i, uid_base=uid_base, want_samples=False)
+    sampler = ClockSampler(local_rank)
+    sync()
+    sampler.start()
+    dev_ms, sims, positions, launches, plies = 0.0, 0, 0, 0, 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        res, st, _ = ctx.selfplay(ROLLOUT, GAMES, cpuct=CPUCT, seed=i, uid_base=uid_base, want_samples=False)
+        assert st["faults"] == 0 and int(res.sum()) == GAMES
+        dev_ms += st["device_ms"]; sims += st["sims"]; positions += st["positions"]; launches += st["kernel_launches"]; plies += st["plies"]
+    sync()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- end to end through the public API with host buffers (e2e) ----
+    cap = GAMES * spec.maxLengthGame
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    bufs = dict(state=pin((cap, 2 * spec.VectorizedState), torch.int8), policy=pin((cap, spec.maxActions), torch.float32), player=pin((cap,), torch.int8),
+                value=pin((cap,), torch.float32), fstate=pin((cap, spec.FeatureSize), torch.int8), game=pin((cap,), torch.int32), ply=pin((cap,), torch.int32))
+    ctx.set_weights(net); ctx.selfplay(ROLLOUT, GAMES, cpuct=CPUCT, seed=77, uid_base=uid_base, out=bufs)      # warm
+    sync()
+    e2e_t0 = time.perf_counter()
+    e2e_sims, d2h, h2d = 0, 0, 0
+    for i in range(args.steps):
+        ctx.set_weights(net)                                                     # H2D: the actor's weights, every step
+        res, st, smp = ctx.selfplay(ROLLOUT, GAMES, cpuct=CPUCT, seed=i, uid_base=uid_base, out=bufs)   # D2H: every sample
+        e2e_sims += st["sims"]
+        d2h += sum(v.nbytes for v in smp.values()) + 24
+        h2d += net.nbytes
+    sync()
+    e2e_wall = time.perf_counter() - e2e_t0
+
+    # ---- per-kernel CUDA-event times on the launching stream (roofline) ----
+    ctx.profile(True)
+    ctx.kernel_times(reset=True)
+    _, pst, _ = ctx.selfplay(ROLLOUT, GAMES, cpuct=CPUCT, seed=0, uid_base=uid_base, want_samples=False)
+    kt = ctx.kernel_times()
+    ctx.profile(False)
+    lay = ctx.layout()
+    ctx.close()
+
+    # ---- reduce over ranks: time = max, work = sum ----
+    if world > 1:
+        t = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        w = torch.tensor([sims, positions, launches, e2e_sims, d2h, h2d], dtype=torch.float64, device="cuda")
+        dist.all_reduce(w, op=dist.ReduceOp.SUM)
+        dev_ms, wall, e2e_wall = [float(x) for x in t.tolist()]
+        sims, positions, launches, e2e_sims, d2h, h2d = [int(x) for x in w.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm, tflops, peak_src = peaks()
+    dbar = kt["nodes_traversed"] / max(1, kt["descents"])
+    S = 18                                                                       # packed Connect4 state: 2 x u64 + player + round
+    per_sim = algorithmic_bytes_per_sim(spec.maxActions, S, dbar)
+    classes = {k: v for k, v in kt.items() if isinstance(v, dict) and v["launches"]}
+    total_ms = sum(v["ms"] for v in classes.values())
+    dom = max(("select", "expand_backup"), key=lambda k: classes[k]["ms"])
+    dom_ms = classes[dom]["ms"]
+    achieved = per_sim[dom] * pst["sims"] / (dom_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
+            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    f_sim = 2 * (2 * spec.VectorizedState * WIDTH + BLOCKS * WIDTH * WIDTH + WIDTH * (spec.maxActions + 1))
+    nn_tf = f_sim * pst["sims"] / (classes["nn"]["ms"] * 1e-3) / 1e12
+
+    line = {
+        "metric": METRIC, "value": sims / (dev_ms * 1e-3), "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {2: "f16 operands / f32 accumulate (tcgen05)", 0: "bf16 operands / f32 accumulate (tcgen05)", 1: "f32"}[args.nn_mode] + "; search f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "games_per_gpu": GAMES, "rollouts": ROLLOUT, "net": "DenseNet 128x6 random-init (Glorot), seed 0", "cpuct": CPUCT,
+                   "l2": "inputs_larger_than_l2 (tree arrays 268 MB per GPU)", "timing": "cuda events on the library stream, max over ranks",
+                   "positions_per_sec": positions / (dev_ms * 1e-3), "mean_game_length": positions / (GAMES * args.steps * world), "d_bar": dbar,
+                   "wall_ms_per_step": 1e3 * wall / args.steps, "node_bytes": lay["node_bytes"], "lanes_per_game": lay["lanes_per_game"]},
+        "clocks": clocks,
+        "e2e": {"value": e2e_sims / e2e_wall, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps // world, "d2h_bytes_per_step": d2h // args.steps // world,
+                "ms_per_step": 1e3 * e2e_wall / args.steps},
+        "gpu_launches": launches,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                     "peak_source": peak_src, "bytes_per_sim": per_sim[dom], "avg_launch_us": 1e3 * dom_ms / classes[dom]["launches"],
+                     "share_of_step": dom_ms / total_ms,
+                     "note": "issue/latency-bound, not HBM-bound: see profiles/ (DRAM throughput 3% of peak, issue slots 50% busy)"},
+        "roofline_nn": {"kernel": "nn (tcgen05 chain)", "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
+                        "flop_per_sim": f_sim, "avg_launch_us": 1e3 * classes["nn"]["ms"] / classes["nn"]["launches"], "share_of_step": classes["nn"]["ms"] / total_ms},
+        "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
+    }
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample (N=1 only) ----
+    if world == 1 and not args.no_cpu_baseline:
+        import oracle
+        ospec = oracle.Spec(oracle.CONNECT4)
+        onet = oracle.Net(net.base, net.res, net.policy, net.policy_bias, net.value, net.value_bias)
+        oracle.selfplay(ospec, onet, ROLLOUT, 32, cpuct=CPUCT, seed=0)           # warm the threads
+        games = 1024
+        t = time.perf_counter()
+        _, ost = oracle.selfplay(ospec, onet, ROLLOUT, games, cpuct=CPUCT, seed=0)
+        dt = time.perf_counter() - t
+        line["cpu_baseline"] = {"value": ost["sims"] / dt, "unit": "sims/s", "cores": oracle.num_threads(), "kind": "port",
+                                "sample": f"{games} of {GAMES} Connect4 games played to the end, same net in fp32, {ost['sims']} sims in {dt:.1f} s"}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
