@@ -172,6 +172,8 @@ int agpu_layout_info(agpu_ctx* ctx, int64_t* node_bytes, int64_t* game_bytes, in
   CTX_OR_FAIL();
   return ctx->eng->layout_info(node_bytes, game_bytes, lanes_per_game);
 }
+/* development hook: device buffer receiving clock64 stamps of the tensor-core chain ([cta][tile][16 layers][4]); NULL disables */
+int agpu_debug_tc_trace(void* dev_buf) { ag::g_tc_dbg = (long long*)dev_buf; return AGPU_OK; }
 /* test hook: the canonical exp / sigmoid evaluated on the device */
 int agpu_debug_expf(agpu_ctx* ctx, const float* x, int64_t n, float* y, int32_t sigmoid) {
   CTX_OR_FAIL();

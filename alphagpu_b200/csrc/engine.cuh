@@ -107,6 +107,8 @@ struct EngineT : EngineBase {
   DevBuf<int8_t> game_result, d_i8;
   DevBuf<int32_t> d_i32;
   DevBuf<unsigned long long> tallies, counters;
+  DevBuf<uint8_t> path_node, path_move, path_len;
+  float last_cpuct = 2.0f;   // cpuct of the most recent descent: the backup re-solves π̄ with it (FAST layouts)
   int32_t* total_host = nullptr;   // pinned
   unsigned long long* tallies_host = nullptr;
   NetSlot nets[2];
@@ -126,7 +128,7 @@ struct EngineT : EngineBase {
     if (stream) cudaStreamSynchronize(stream);
     for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    tree.release(); nnodes.release(); leaf.release(); block_count.release(); total_dev.release(); uid.release(); uid_b.release();
+    path_node.release(); path_move.release(); path_len.release(); tree.release(); nnodes.release(); leaf.release(); block_count.release(); total_dev.release(); uid.release(); uid_b.release();
     policy_final.release(); nn_out.release(); d_prob.release(); d_prior.release(); d_value.release(); d_fscratch.release();
     st_a.release(); st_b.release(); game_final.release(); alive.release(); d_u8.release(); game_result.release(); d_i8.release();
     d_i32.release(); tallies.release(); counters.release();
@@ -189,6 +191,8 @@ struct EngineT : EngineBase {
     AG_CK(st_a.ensure(L_cap)); AG_CK(st_b.ensure(L_cap)); AG_CK(alive.ensure(L_cap));
     AG_CK(block_count.ensure((L_cap + 255) / 256 + 1)); AG_CK(total_dev.ensure(1));
     AG_CK(tallies.ensure(8)); AG_CK(counters.ensure(2));
+    AG_CK(path_node.ensure((size_t)L_cap * R)); AG_CK(path_move.ensure((size_t)L_cap * R)); AG_CK(path_len.ensure(L_cap));
+    AG_CK(cudaMemsetAsync(path_len.p, 0, L_cap, stream));
     AG_CK(cudaMallocHost((void**)&total_host, sizeof(int32_t)));
     AG_CK(cudaMallocHost((void**)&tallies_host, 8 * sizeof(unsigned long long)));
     AG_CK(cudaMemsetAsync(tree.p, 0, (size_t)L_cap * R * Lay::REC, stream));
@@ -197,6 +201,7 @@ struct EngineT : EngineBase {
     AG_CK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), stream));
     P.tree = tree.p; P.game_stride = (size_t)R * Lay::REC; P.R = R; P.nnodes = nnodes.p; P.leaf = leaf.p; P.uid = uid.p;
     P.policy_final = policy_final.p; P.nn_out = nn_out.p; P.counters = nullptr;
+    P.path_node = path_node.p; P.path_move = path_move.p; P.path_len = path_len.p;
     AG_CK(cudaStreamSynchronize(stream));
     return AGPU_OK;
   }
@@ -370,22 +375,34 @@ struct EngineT : EngineBase {
   }
 
   void launch_select(int64_t L, int rollout, int last, float cpuct, const float* dprob, uint64_t seed, uint32_t ply) {
+    last_cpuct = cpuct;
     launch(K_SELECT, [&] { select_kernel<G><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, rollout, last, cpuct, dprob, seed, ply); });
   }
   void launch_expand(int64_t L, int training, int last, const float* dprior, const float* dvalue) {
-    if (dprior) launch(K_EXPAND, [&] { expand_backup_kernel<G, true><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, training, last, dprior, dvalue); });
-    else launch(K_EXPAND, [&] { expand_backup_kernel<G, false><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, training, last, nullptr, nullptr); });
+    if (dprior) launch(K_EXPAND, [&] { expand_backup_kernel<G, true><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, training, last, dprior, dvalue, last_cpuct); });
+    else launch(K_EXPAND, [&] { expand_backup_kernel<G, false><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, training, last, nullptr, nullptr, last_cpuct); });
   }
 
-  // the rollout loop of mcts_single (mcts_gpu.jl:396-439), no host synchronisation inside
+  void launch_step(int64_t L, int rollout, int last, int training, float cpuct, uint64_t seed, uint32_t ply) {
+    last_cpuct = cpuct;
+    launch(K_SELECT, [&] { step_kernel<G><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, rollout, last, training, cpuct, seed, ply); });
+  }
+
+  // the rollout loop of mcts_single (mcts_gpu.jl:396-439), no host synchronisation inside.  With the in-kernel RNG the
+  // search side is one launch per rollout: [expand+backUp of rollout k-1 | descent of rollout k].
   int enqueue_search(int64_t L, int slot, int visits, int training, float cpuct, const float* dprob, uint64_t seed, uint32_t ply) {
     NNInput I = nn_input_tree();
     for (int k = 0; k < visits; k++) {
       const int last = (k == visits - 1);
-      launch_select(L, k, last, cpuct, dprob, seed, ply);
+      if (dprob) {
+        launch_select(L, k, last, cpuct, dprob, seed, ply);
+      } else {
+        if (k == 0) launch_select(L, 0, last, cpuct, nullptr, seed, ply);
+        else launch_step(L, k, last, training, cpuct, seed, ply);
+      }
       int rc = run_nn(slot, I, L, nn_out.p, Lay::OUTS);
       if (rc != AGPU_OK) return rc;
-      launch_expand(L, training, last, nullptr, nullptr);
+      if (dprob || last) launch_expand(L, training, last, nullptr, nullptr);
     }
     AG_CK(cudaGetLastError());
     return AGPU_OK;
@@ -434,6 +451,7 @@ struct EngineT : EngineBase {
       dprob = d_prob.p;
     }
     // the kernel indexes prob by (rollout*L + g): pass rollout 0 for the slice, keep the RNG counter separately
+    last_cpuct = cpuct;
     if (dprob) launch(K_SELECT, [&] { select_kernel<G><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, 0, last, cpuct, dprob, seed, ply); });
     else launch_select(L, rollout, last, cpuct, nullptr, seed, ply);
     AG_CK(cudaGetLastError());

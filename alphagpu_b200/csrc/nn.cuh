@@ -115,5 +115,6 @@ size_t tc_image_bytes(int in, int n, int k, int A);
 void tc_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
                     const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host, int fmt);
 cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt);
+extern long long* g_tc_dbg;
 
 }  // namespace ag

@@ -3,16 +3,16 @@
 // One CTA evaluates 256 leaf positions (two M=128 tiles) through ALL layers without touching HBM in
 // between:  x -> relu(W0 x) -> k x [ b = relu(b + relu(W b)) ] -> (policy | value) heads.
 //
-//   warps 0-3  : tile 0   } each warpgroup owns one 128-row tile: builds the A operand (0/1 encoding of the
-//   warps 4-7  : tile 1   } leaf bitboards, straight from the tree record), one elected lane issues the
-//                           tcgen05.mma chain of the layer, all 128 threads run the epilogue (tcgen05.ld of
-//                           their TMEM lane, residual/relu in fp32 registers, bf16 repack into the swizzled A
-//                           operand of the next layer).  While one warpgroup is in its epilogue the tensor
-//                           pipe runs the other tile's MMAs.
+//   warps 0-7  : tile 0   } each group of 8 warps owns one 128-row tile: builds the A operand (0/1 encoding of the
+//   warps 8-15 : tile 1   } leaf bitboards, straight from the tree record), one elected lane issues the
+//                           tcgen05.mma chain of the layer, all 256 threads run the epilogue: warp w reads TMEM lane
+//                           quarter w%4 (its rows) and column half w/4 with tcgen05.ld, keeps its 64 columns of the
+//                           residual stream in fp32 registers, and repacks them into the swizzled A operand of the
+//                           next layer.  While one tile is in its epilogue the tensor pipe runs the other tile's MMAs.
 //   weight producer: the issuing lane of tile 0 also streams the per-layer weight images global->shared with 1-D
 //                bulk copies (cp.async.bulk, mbarrier complete_tx) through a 3-stage ring shared by both tiles, two
-//                layers ahead of the MMAs.  (No ninth warp: with 9 warps one SM sub-partition hosts 3 of them and
-//                the register budget drops from 255 to 168 per thread, which spills the fp32 residual row.)
+//                layers ahead of the MMAs (no extra producer warp: 17 warps would put 5 on one SM sub-partition and cut
+//                the register budget below what the fp32 residual columns need).
 //
 // Operands: A (activations) and B (weights) are K-major bf16 with the 128-byte swizzle the UMMA shared-memory
 // descriptor expects (8-row x 128 B atoms, SBO = 1024 B); weights are pre-swizzled on the host into exactly
@@ -37,8 +37,9 @@ constexpr int TC_STAGES = 3;           // weight ring depth
 constexpr int TC_W_STAGE_BYTES = TC_N * TC_N * 2;                    // 32 KB: one 128x128 bf16 layer image
 constexpr int TC_A_BYTES = TC_TILE_M * TC_N * 2;                     // 32 KB per tile
 constexpr int TC_KTILE_BYTES_A = TC_TILE_M * 128;                    // 16 KB: 128 rows x 64 bf16
-constexpr int TC_THREADS = 32 * 4 * TC_TILES;                        // 256: 2 warps per SM sub-partition, so up to 255 registers per thread
-constexpr int TC_SMEM = TC_TILES * TC_A_BYTES + TC_STAGES * TC_W_STAGE_BYTES + 256 + 1024;   // + barriers + alignment slack
+constexpr int TC_WARPS_PER_TILE = 8;                                 // 4 TMEM lane quarters x 2 column halves
+constexpr int TC_THREADS = 32 * TC_WARPS_PER_TILE * TC_TILES;        // 512: 4 warps per SM sub-partition, 128 registers per thread
+constexpr int TC_SMEM = TC_TILES * TC_A_BYTES + TC_STAGES * TC_W_STAGE_BYTES + 1024 + 1024;   // + barriers + alignment slack
 
 __host__ __device__ inline int head_n(int A) { return (A + 1 + 15) / 16 * 16; }
 
@@ -142,6 +143,7 @@ struct TcArgs {
   int A;                      // actions
   int NH;                     // head N (multiple of 16)
   int in;                     // 2*VS
+  long long* dbg;             // optional clock64 trace [cta][tile][layer][4] (development)
 };
 
 template <int FMT>
@@ -152,22 +154,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
   unsigned char* sA = smem;                                          // [2][32 KB]
   unsigned char* sW = smem + TC_TILES * TC_A_BYTES;                  // [3][32 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + TC_STAGES * TC_W_STAGE_BYTES);
-  // bars[0..2] full, [3..5] empty, [6..7] mma_done, then the TMEM base word
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  // bars[0..2] full, [3..5] empty, [6..7] mma_done, [8] stagger (one-shot), then the TMEM base word
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* sbias = reinterpret_cast<float*>(bars + 10);               // [128] head biases
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long* trp = (T.dbg && (warp % TC_WARPS_PER_TILE) == 0 && lane == 0) ? T.dbg + (((size_t)blockIdx.x * TC_TILES + warp / TC_WARPS_PER_TILE) * 16 + 12) * 4 : nullptr;
+  if (trp) trp[0] = clock64();
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, TC_TILES); }
     for (int t = 0; t < TC_TILES; t++) mbar_init(bar_done + 8 * t, 1);
+    mbar_init(bar_full + 8 * 8, 1);
     fence_barrier_init();
   }
+  if (threadIdx.x < TC_N) sbias[threadIdx.x] = T.bias[threadIdx.x];
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (trp) trp[1] = clock64();
 
   // weight image of layer l -> ring stage l % 3 (called by one thread)
   auto load_layer = [&](int l) {
@@ -183,145 +191,173 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
   }
   {
     // ===================== tile warpgroups =====================
-    const int t = warp >> 2;                       // tile of this warpgroup
-    const int r = (warp & 3) * 32 + lane;          // row in tile == TMEM lane
+    const int t = warp / TC_WARPS_PER_TILE;        // tile of this warp group
+    const int wq = warp & 3;                       // TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
+    const int ch = (warp >> 2) & 1;                // column half handled by this warp
+    const int r = wq * 32 + lane;                  // row in tile == TMEM lane
     const int g = blockIdx.x * (TC_TILES * TC_TILE_M) + t * TC_TILE_M + r;
     unsigned char* At = sA + t * TC_A_BYTES;
     const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);                       // column offset of this tile
-    const uint32_t tmem_row = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);          // + lane base of this warp's subpartition
+    const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ch * 64);   // lane base of this warp's quarter, its column half
 
     // ---- A operand of the base layer: 0/1 encoding of the leaf position (decoder, mcts_gpu.jl:202-223) ----
     {
-      u64 b0 = 0, b1 = 0, b2 = 0, b3 = 0, b4 = 0, b5 = 0;
+      u64 b0 = 0, b1 = 0;
       const float* xd = nullptr;
       if (g < L) {
         if (I.x_direct) xd = I.x_direct + (size_t)g * (2 * I.VS);
         else {
           const u64* st = reinterpret_cast<const u64*>(I.tree + (size_t)g * I.game_stride + (size_t)I.leaf[g] * I.rec + I.off_state);
           const int nch = 2 * I.nc;
-          b0 = st[0]; b1 = st[1];
-          if (nch > 2) { b2 = st[2]; b3 = st[3]; }
-          if (nch > 4) { b4 = st[4]; b5 = st[5]; }
+          (void)nch;
+          b0 = st[0]; b1 = st[1];                           // nc == 1 (tc_supported): bplayer, bopponent
         }
       }
-      auto getb = [&](int ci) -> u64 { return ci == 0 ? b0 : ci == 1 ? b1 : ci == 2 ? b2 : ci == 3 ? b3 : ci == 4 ? b4 : b5; };
       const int VS = I.VS, nc = I.nc;
-#pragma unroll 1
-      for (int c = 0; c < 16; c++) {               // 16 chunks of 8 bf16 = K 128
-        uint32_t w[4];
+      if (!xd) {
+        // tree path (2*VS <= 128 => one 64-bit chunk per board): x = [bplayer bits 0..VS-1 | bopponent bits 0..VS-1] as a
+        // 128-bit vector; each pair of bits becomes one packed pair of 0.0/1.0 operands
+        const u64 bp = b0, bo = b1;
+        const u64 x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
+        const u64 x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
+        const u64 xh = ch ? x1 : x0;                       // this warp's K tile = operand bits 64*ch .. 64*ch+63
+        const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-          float f[2];
+        for (int cl = 0; cl < 8; cl++) {
+          const uint32_t byte = (uint32_t)(xh >> (8 * cl)) & 0xFFu;
+          uint32_t w[4];
 #pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int k = c * 8 + e * 2 + h;
-            float v = 0.f;
-            if (k < 2 * VS && g < L) {
-              if (xd) v = xd[k];
-              else {
-                const int kk = k < VS ? k : k - VS;
-                const int ci = (k < VS ? 0 : nc) + (kk >> 6);
-                v = ((getb(ci) >> (kk & 63)) & 1) ? 1.f : 0.f;
-              }
-            }
-            f[h] = v;
-          }
-          w[e] = pack2<FMT>(f[0], f[1]);
+          for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
+          *reinterpret_cast<uint4*>(At + ch * TC_KTILE_BYTES_A + r * 128 + ((cl ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
-        const int ktile = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      } else {
+#pragma unroll 1
+        for (int c = 8 * ch; c < 8 * ch + 8; c++) {  // this warp's 8 chunks of 8 operands (K tile `ch`)
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int k = c * 8 + e * 2;
+            const float f0 = (k < 2 * VS && g < L) ? xd[k] : 0.f;
+            const float f1 = (k + 1 < 2 * VS && g < L) ? xd[k + 1] : 0.f;
+            w[e] = pack2<FMT>(f0, f1);
+          }
+          const int ktile = c >> 3, cc = c & 7;
+          *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
+      (void)nc;
     }
     fence_proxy_async();
-    named_bar_sync(1 + t, 128);
+    named_bar_sync(1 + t, 32 * TC_WARPS_PER_TILE);
+    if (trp) trp[2] = clock64();
 
-    float h[TC_N];                                   // fp32 residual stream of this row
+    float h[TC_N / 2];                                   // fp32 residual stream of this row
 #pragma unroll
-    for (int i = 0; i < TC_N; i++) h[i] = 0.f;
+    for (int i = 0; i < TC_N / 2; i++) h[i] = 0.f;
 
     for (int l = 0; l < T.nlayers; l++) {
       const int s = l % TC_STAGES;
       const bool is_head = (l == T.nlayers - 1);
       const int nl = is_head ? T.NH : TC_N;
-      if ((warp & 3) == 0 && lane == 0) {
+      const bool tracer = T.dbg && (warp % TC_WARPS_PER_TILE) == 0 && lane == 0;
+      long long* tr = T.dbg ? T.dbg + (((size_t)blockIdx.x * TC_TILES + t) * 16 + l) * 4 : nullptr;
+      if (tracer) tr[0] = clock64();
+      if ((warp % TC_WARPS_PER_TILE) == 0 && lane == 0) {
         // ---- MMA issue: D[128 x nl] = A[128 x K] * W_l[nl x K]^T ----
         mbar_wait(bar_full + 8 * s, (l / TC_STAGES) & 1);
+        // stagger: tile 1 issues its first layer only after tile 0's first layer has drained, so that from then on one tile's
+        // MMAs run while the other tile is in its epilogue (in lockstep both would share the tensor pipe, then both leave it idle)
+        // (a one-shot barrier: its phase 0 completes once and never flips back, so a late tile 1 can not miss it)
+        if (l == 0 && t == 1) mbar_wait(bar_full + 8 * 8, 0);
         tc_fence_after();
-        const int ksteps = (l == 0) ? T.k0_steps : TC_N / 16;
-        const uint32_t a0 = smem_u32(At), b0 = smem_u32(sW + s * TC_W_STAGE_BYTES);
+        // 8 K-steps of 16 (the base layer's operands are zero-padded to K = 128).  Fully unrolled with precomputed descriptor
+        // increments: a single thread issues these, and a rolled loop with per-step descriptor arithmetic measured ~180 cycles
+        // per MMA against the tensor pipe's 64 (profiles/r01_tc_trace.txt).
+        const uint64_t ad0 = umma_desc(smem_u32(At));
+        const uint64_t bd0 = umma_desc(smem_u32(sW + s * TC_W_STAGE_BYTES));
         const uint32_t idesc = umma_idesc<FMT>(nl);
-        for (int ks = 0; ks < ksteps; ks++) {
-          const int ktile = ks >> 2, kin = ks & 3;
-          const uint64_t ad = umma_desc(a0 + ktile * TC_KTILE_BYTES_A + kin * 32);
-          const uint64_t bd = umma_desc(b0 + ktile * (nl * 128) + kin * 32);
-          umma_bf16(tmem_acc, ad, bd, idesc, ks > 0 ? 1u : 0u);
+        const uint64_t bstep = (uint64_t)((nl * 128) >> 4);              // second K tile of the weight image
+#pragma unroll
+        for (int ks = 0; ks < TC_N / 16; ks++) {
+          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+          umma_bf16(tmem_acc, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
         }
         umma_commit(bar_done + 8 * t);               // accumulator ready -> epilogue of this tile
         umma_commit(bar_empty + 8 * s);              // weight stage consumed by this tile
+        if (l == 0 && t == 0) umma_commit(bar_full + 8 * 8);
         if (t == 0 && l + 2 < T.nlayers) load_layer(l + 2);   // producer role: keep the ring two layers ahead
+        if (tracer) tr[1] = clock64();
       }
       mbar_wait(bar_done + 8 * t, l & 1);
       tc_fence_after();
+      if (tracer) tr[2] = clock64();
 
       if (!is_head) {
         // ---- epilogue: b = relu(acc) (base) or relu(b + relu(acc)); next A operand = bf16/fp16(b) ----
         uint32_t va[16], vb[16];
-        auto process = [&](const int cb, const uint32_t (&cur)[16]) {      // columns 16*cb .. 16*cb+15
+        auto process = [&](const int cb, const uint32_t (&cur)[16]) {      // this warp's columns 64*ch + 16*cb .. +15
 #pragma unroll
           for (int i = 0; i < 16; i++) {
             const float ra = fmaxf(__uint_as_float(cur[i]), 0.f);
-            h[cb * 16 + i] = (l == 0) ? ra : fmaxf(h[cb * 16 + i] + ra, 0.f);
+            // relu(b + relu(acc)) == b + relu(acc): b >= 0 by induction from b0 = relu(.), so the outer relu is the identity
+            h[cb * 16 + i] = (l == 0) ? ra : h[cb * 16 + i] + ra;
           }
 #pragma unroll
           for (int c2 = 0; c2 < 2; c2++) {           // 2 chunks of 8 columns
-            const int c = cb * 2 + c2;               // chunk index in the row, 0..15
-            const uint4 pk = make_uint4(pack2<FMT>(h[c * 8 + 0], h[c * 8 + 1]), pack2<FMT>(h[c * 8 + 2], h[c * 8 + 3]),
-                                        pack2<FMT>(h[c * 8 + 4], h[c * 8 + 5]), pack2<FMT>(h[c * 8 + 6], h[c * 8 + 7]));
-            const int ktile = c >> 3, cc = c & 7;
-            *reinterpret_cast<uint4*>(At + ktile * TC_KTILE_BYTES_A + r * 128 + ((cc ^ (r & 7)) << 4)) = pk;
+            const int cl = cb * 2 + c2;              // chunk within this warp's half, 0..7
+            const uint4 pk = make_uint4(pack2<FMT>(h[cl * 8 + 0], h[cl * 8 + 1]), pack2<FMT>(h[cl * 8 + 2], h[cl * 8 + 3]),
+                                        pack2<FMT>(h[cl * 8 + 4], h[cl * 8 + 5]), pack2<FMT>(h[cl * 8 + 6], h[cl * 8 + 7]));
+            *reinterpret_cast<uint4*>(At + ch * TC_KTILE_BYTES_A + r * 128 + ((cl ^ (r & 7)) << 4)) = pk;   // K tile == column half
           }
         };
         // the TMEM load of the next 16 columns is in flight while the current ones are processed
         tmem_ld16(tmem_row, va);
 #pragma unroll
-        for (int cb = 0; cb < TC_N / 16; cb += 2) {
+        for (int cb = 0; cb < 4; cb += 2) {
           tmem_ld_wait();
           tmem_ld16(tmem_row + (cb + 1) * 16, vb);
           process(cb, va);
           tmem_ld_wait();
-          if (cb + 2 < TC_N / 16) tmem_ld16(tmem_row + (cb + 2) * 16, va);
+          if (cb + 2 < 4) tmem_ld16(tmem_row + (cb + 2) * 16, va);
           process(cb + 1, vb);
         }
         tc_fence_before();
         fence_proxy_async();
-        named_bar_sync(1 + t, 128);
+        named_bar_sync(1 + t, 32 * TC_WARPS_PER_TILE);
+        if (tracer) tr[3] = clock64();
       } else {
         // ---- heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) ----
         float* o = out + (size_t)g * outs;
-        for (int cb = 0; cb * 32 < T.NH; cb++) {
-          uint32_t v[32];
-          tmem_ld32(tmem_row + cb * 32, v);
+        for (int cb = 0; cb < 4 && ch * 64 + cb * 16 < T.NH; cb++) {     // warp-uniform bounds
+          uint32_t v[16];
+          tmem_ld16(tmem_row + cb * 16, v);
           tmem_ld_wait();
+          const int a0 = ch * 64 + cb * 16;
+          float z[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) z[i] = __uint_as_float(v[i]) + sbias[a0 + i];
+          if (T.A >= a0 && T.A < a0 + 16) {                              // the value column lives in this group of 16 (warp-uniform)
+#pragma unroll
+            for (int i = 0; i < 16; i++) if (a0 + i == T.A) z[i] = c_sigmoidf(z[i]);
+          }
           if (g < L) {
 #pragma unroll
-            for (int i = 0; i < 32; i++) {
-              const int a = cb * 32 + i;
-              if (a <= T.A) {
-                const float z = __uint_as_float(v[i]) + T.bias[a];
-                o[a] = (a == T.A) ? c_sigmoidf(z) : z;
-              }
-            }
+            for (int q4 = 0; q4 < 4; q4++)
+              if (a0 + 4 * q4 < outs) *reinterpret_cast<float4*>(o + a0 + 4 * q4) = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
           }
         }
         tc_fence_before();
       }
     }
   }
+  if (trp) trp[3] = clock64();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
+  if (trp) trp[4] = clock64();
 }
 
 inline uint16_t f2bf(float f) {
@@ -399,6 +435,8 @@ void tc_build_image(const float* base, const float* const* res, const float* pol
   bias_host[A] = val_b[0];
 }
 
+long long* g_tc_dbg = nullptr;   // development: set through agpu_debug_tc_trace
+
 cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt) {
   static bool attr_set = false;
   if (!attr_set) {
@@ -410,6 +448,7 @@ cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, i
   TcArgs T;
   T.img = (const unsigned char*)net.tc_img; T.bias = net.tc_bias; T.nlayers = net.k + 2; T.k0_steps = (net.in + 15) / 16; T.A = net.A;
   T.NH = head_n(net.A); T.in = net.in;
+  T.dbg = g_tc_dbg;
   const int grid = (L + TC_TILES * TC_TILE_M - 1) / (TC_TILES * TC_TILE_M);
   if (fmt == 0) tc_mlp128_kernel<0><<<grid, TC_THREADS, TC_SMEM, stream>>>(T, I, L, out, outs);
   else tc_mlp128_kernel<1><<<grid, TC_THREADS, TC_SMEM, stream>>>(T, I, L, out, outs);

@@ -41,6 +41,10 @@ constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 #ifndef AG_LANES_SHIFT
 #define AG_LANES_SHIFT 0
 #endif
+// resident 256-thread blocks per SM the search kernels are compiled for (register cap = 65536 / (256 * AG_MINBLOCKS))
+#ifndef AG_MINBLOCKS
+#define AG_MINBLOCKS 4
+#endif
 template <class G>
 struct Layout {
   static constexpr int A = G::A;
@@ -54,7 +58,13 @@ struct Layout {
   static constexpr int OFF_VIS = 8 * APAD;
   static constexpr int OFF_CHILD = 10 * APAD;
   static constexpr int OFF_ORDER = 11 * APAD;
-  static constexpr int OFF_STATE = (12 * APAD + 7) / 8 * 8;
+  // Small action sets (Connect4, tic-tac-toe): π̄ is stored per node and re-solved in the BACKUP phase, one lane per ancestor,
+  // all ancestors of a path in parallel; the descent then only samples.  Equivalent to the reference's solve-at-descent because
+  // a node's statistics change only when a backup passes through it (sticky `uptodate`, mcts_gpu.jl:114,321) and the solve is a
+  // pure function of them.  Large action sets keep the cooperative solve-at-descent (the network dominates there).
+  static constexpr bool FAST = (A <= 9);
+  static constexpr int OFF_POLICY = (12 * APAD + 15) / 16 * 16;
+  static constexpr int OFF_STATE = FAST ? OFF_POLICY + 4 * APAD : (12 * APAD + 7) / 8 * 8;
   static constexpr int OFF_HDR = OFF_STATE + (int)sizeof(typename G::State);
   static constexpr int REC = (OFF_HDR + 8 + 31) / 32 * 32;         // record size, multiple of a 32 B sector
   static constexpr int OUTS = (A + 1 + 3) / 4 * 4;                 // floats per game of network output: logits[A], value
@@ -71,6 +81,10 @@ struct SearchParams {
   float* policy_final;   // [L][A]
   float* nn_out;         // [L][OUTS] logits then value
   unsigned long long* counters;   // [2] nodes traversed, descents (profiling; may be null)
+  // path of the last descent (FAST layouts): node ids (0-based) and actions (0-based) from the root down to the leaf's parent
+  uint8_t* path_node;    // [L][R]
+  uint8_t* path_move;    // [L][R]
+  uint8_t* path_len;     // [L]
 };
 
 template <int W> AG_D unsigned group_mask() {
@@ -122,17 +136,69 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// The α-solve of kdescendTree! (mcts_gpu.jl:116-169) for ONE node by ONE lane, everything in registers.  Same operations in the
+// same order as the reference loop: sums ascending in the action, Newton terms in child-creation order starting from prior_rem/α.
+// vis = visits after the update; ord[k] = 1-based action of the k-th created child.
+// ------------------------------------------------------------------------------------------------
+template <int A, int AP>
+AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis)[AP], const int (&ch)[AP], const int (&ord)[AP],
+                     const int nchild, const float cpuct, float (&pol)[AP]) {
+  int nv = 0, acount = 0;
+  float rem = 0.f;
+#pragma unroll
+  for (int a = 0; a < A; a++) {
+    nv += vis[a];
+    rem = fadd(rem, ch[a] == 0 ? p[a] : 0.f);
+    acount += p[a] > 0.f ? 1 : 0;
+  }
+  const float n = (float)(1 + nv);
+  const float lambda = fdiv(fmul(cpuct, fsqrt(n)), fadd((float)acount, n));      // :132
+  rem = fmul(rem, lambda);                                                          // :134
+  float alpha = 0.f, top[AP];
+#pragma unroll
+  for (int a = 0; a < A; a++) {
+    top[a] = fmul(lambda, p[a]);
+    alpha = fmaxf(alpha, fadd(q[a], fmaxf(top[a], 1e-4f)));                          // :135-138
+  }
+  // statistics of the children in slot order (static selects instead of dynamically indexed registers)
+  float tops[AP], qs[AP];
+#pragma unroll
+  for (int k = 0; k < A; k++) {
+    tops[k] = 0.f; qs[k] = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; a++) if (ord[k] == a + 1) { tops[k] = top[a]; qs[k] = q[a]; }
+  }
+  float err = __int_as_float(0x7f800000);
+  for (int it = 0; it < 100; it++) {                                                 // :141-162
+    float S = fdiv(rem, alpha);
+    float gs = fdiv(-rem, fmul(alpha, alpha));
+#pragma unroll
+    for (int k = 0; k < A; k++) {
+      if (k < nchild) {
+        const float bot = fsub(alpha, qs[k]);
+        S = fadd(S, fdiv(tops[k], bot));
+        gs = fadd(gs, fdiv(-tops[k], fmul(bot, bot)));
+      }
+    }
+    const float newerr = fsub(S, 1.f);
+    if (newerr < 0.001f || newerr == err) break;
+    alpha = fsub(alpha, fdiv(newerr, gs));
+    err = newerr;
+  }
+#pragma unroll
+  for (int a = 0; a < A; a++) pol[a] = fdiv(top[a], fsub(alpha, q[a]));              // :165-169
+#pragma unroll
+  for (int a = A; a < AP; a++) pol[a] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // select: kdescendTree! (mcts_gpu.jl:100-199).  One group of W lanes per game.
 // ------------------------------------------------------------------------------------------------
 template <class G>
-__global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int rollout, int last_rollout, float cpuct,
-                                                     const float* __restrict__ prob, u64 seed, u32 ply) {
+AG_D void select_game(const SearchParams& P, const int g, const int l, const unsigned gm, int L, int rollout, int last_rollout, float cpuct,
+                      const float* __restrict__ prob, u64 seed, u32 ply) {
   typedef Layout<G> Lay;
   constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
-  const int l = threadIdx.x & (W - 1);
-  if (g >= L) return;
-  const unsigned gm = group_mask<W>();
   char* gbase = P.tree + (size_t)g * P.game_stride;
   int nn = P.nnodes[g];
   const u32 uid = P.uid[g];
@@ -146,6 +212,11 @@ __global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int 
 
     float p[APL], q[APL], pol[APL];
     int vis[APL], ch[APL], ord[APL];
+    if constexpr (Lay::FAST) {
+      static_assert(APL == 1, "FAST layouts have one action per lane");
+      pol[0] = l < A ? *reinterpret_cast<const float*>(rec + Lay::OFF_POLICY + 4 * l) : 0.f;   // π̄ as left by expand / the last backup
+      ch[0] = l < A ? (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_CHILD + l) : 0;
+    } else {
 #pragma unroll
     for (int j = 0; j < APL; j++) {
       const int a = j * W + l;
@@ -213,6 +284,7 @@ __global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int 
 #pragma unroll
       for (int j = 0; j < APL; j++) pol[j] = p[j];                                  // policy == prior until the first backup (:297-299)
     }
+    }   // !FAST
 
     if (node == 0 && last_rollout) {                                                 // copy_pol (:330-339): π̄_root of the last descent
 #pragma unroll
@@ -246,6 +318,10 @@ __global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int 
       }
     }
     if (best < 0) best = 0;
+    if (Lay::FAST && l == 0) {                                                        // remember the path for the lane-parallel backup
+      P.path_node[(size_t)g * P.R + depth] = (uint8_t)node;
+      P.path_move[(size_t)g * P.R + depth] = (uint8_t)best;
+    }
     int c = gshfl<W>(gm, pick<APL>(ch, best / W), best % W);
     if (c == 0) {                                                                     // allocate the child (:183-191)
       nn += 1;
@@ -281,8 +357,18 @@ __global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int 
   if (l == 0) {
     P.leaf[g] = node;                                                                  // :195
     P.nnodes[g] = nn;
+    if (Lay::FAST) P.path_len[g] = (uint8_t)depth;
     if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)depth); atomicAdd(&P.counters[1], 1ull); }
   }
+}
+
+template <class G>
+__global__ void __launch_bounds__(256, AG_MINBLOCKS) select_kernel(SearchParams P, int L, int rollout, int last_rollout, float cpuct,
+                                                     const float* __restrict__ prob, u64 seed, u32 ply) {
+  constexpr int W = Layout<G>::W;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  if (g >= L) return;
+  select_game<G>(P, g, threadIdx.x & (W - 1), group_mask<W>(), L, rollout, last_rollout, cpuct, prob, seed, ply);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -290,14 +376,10 @@ __global__ void __launch_bounds__(256) select_kernel(SearchParams P, int L, int 
 // INJECT: prior_in[L][A] is already softmaxed (what `expand` receives), value_in[L].
 // ------------------------------------------------------------------------------------------------
 template <class G, bool INJECT>
-__global__ void __launch_bounds__(256) expand_backup_kernel(SearchParams P, int L, int training, int last_rollout,
-                                                            const float* __restrict__ prior_in, const float* __restrict__ value_in) {
+AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, const unsigned gm, int training, int last_rollout,
+                             const float* __restrict__ prior_in, const float* __restrict__ value_in, const float cpuct) {
   typedef Layout<G> Lay;
   constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
-  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
-  const int l = threadIdx.x & (W - 1);
-  if (g >= L) return;
-  const unsigned gm = group_mask<W>();
   char* gbase = P.tree + (size_t)g * P.game_stride;
   const int leaf = P.leaf[g];
   char* rec = gbase + (size_t)leaf * REC;
@@ -351,12 +433,82 @@ __global__ void __launch_bounds__(256) expand_backup_kernel(SearchParams P, int 
       float pr = 0.f;
       if (legal[j]) pr = rootmix ? fadd(fdiv(fmul(0.75f, pin[j]), normalize), unif) : fdiv(pin[j], normalize);
       *reinterpret_cast<float*>(rec + Lay::OFF_PRIOR + 4 * a) = pr;
+      if (Lay::FAST) *reinterpret_cast<float*>(rec + Lay::OFF_POLICY + 4 * a) = pr;      // policy[:,leaf] = prior[:,leaf]  (:297-299)
       if (leaf == 0 && last_rollout && a < A) P.policy_final[(size_t)g * A + a] = pr;    // R == 1: policy[:,1] is the prior itself
     }
     if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
   }
 
   // backUp: :306-328
+  if constexpr (Lay::FAST) {
+    // Lane-parallel backup: lane jj takes the jj-th node of the recorded path (0 = root).  Each ancestor is a different node, so
+    // the running-mean updates are independent; the value each one receives is the leaf value flipped once per level below it
+    // (value = 1 - value, :324), evaluated as that literal chain.  The lane then re-solves π̄ of its node (solve_node) — except
+    // after the last rollout, whose π̄ nobody reads (policy_final is the root policy of the last DESCENT, :443).
+    constexpr int AP = Lay::APAD;
+    const int d = P.path_len[g];
+    const double value0_d = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;   // terminal: Float64 in the reference (:314)
+    for (int base = 0; base < d; base += W) {
+      const int jj = base + l;
+      if (jj < d) {
+        const int flips = d - 1 - jj;
+        const int nd = P.path_node[(size_t)g * P.R + jj];
+        const int mv = P.path_move[(size_t)g * P.R + jj];
+        char* nrec = gbase + (size_t)nd * REC;
+        float p[AP], q[AP], pol[AP];
+        int vis[AP], ch[AP], ord[AP];
+#pragma unroll
+        for (int c = 0; c < AP / 4; c++) {
+          const float4 pv = *reinterpret_cast<const float4*>(nrec + Lay::OFF_PRIOR + 16 * c);
+          const float4 qv = *reinterpret_cast<const float4*>(nrec + Lay::OFF_Q + 16 * c);
+          p[4 * c] = pv.x; p[4 * c + 1] = pv.y; p[4 * c + 2] = pv.z; p[4 * c + 3] = pv.w;
+          q[4 * c] = qv.x; q[4 * c + 1] = qv.y; q[4 * c + 2] = qv.z; q[4 * c + 3] = qv.w;
+        }
+#pragma unroll
+        for (int c = 0; c < AP / 8; c++) {
+          const uint4 vv = *reinterpret_cast<const uint4*>(nrec + Lay::OFF_VIS + 16 * c);
+          const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) { vis[8 * c + 2 * e] = (int)(w4[e] & 0xFFFFu); vis[8 * c + 2 * e + 1] = (int)(w4[e] >> 16); }
+        }
+#pragma unroll
+        for (int c = 0; c < AP / 8; c++) {          // child bytes then order bytes, AP bytes each, contiguous
+          const uint2 cv = *reinterpret_cast<const uint2*>(nrec + Lay::OFF_CHILD + 8 * c);
+          const uint2 ov = *reinterpret_cast<const uint2*>(nrec + Lay::OFF_ORDER + 8 * c);
+          const uint32_t cw[2] = {cv.x, cv.y}, ow[2] = {ov.x, ov.y};
+#pragma unroll
+          for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
+        }
+        const int nchild = reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR)->nchild;
+        // running mean of the child's value from this node's point of view (:319-320)
+        float qold = 0.f; int vold = 0;
+#pragma unroll
+        for (int a = 0; a < A; a++) if (a == mv) { qold = q[a]; vold = vis[a]; }
+        const float vf = (float)vold;
+        float qnew;
+        if (term) {
+          double val = value0_d;
+          for (int t = 0; t < flips; t++) val = __dsub_rn(1.0, val);
+          qnew = (float)__ddiv_rn(__dadd_rn((double)fmul(vf, qold), __dsub_rn(1.0, val)), (double)fadd(vf, 1.f));
+        } else {
+          float val = v;
+          for (int t = 0; t < flips; t++) val = fsub(1.f, val);
+          qnew = fdiv(fadd(fmul(vf, qold), fsub(1.f, val)), fadd(vf, 1.f));
+        }
+#pragma unroll
+        for (int a = 0; a < A; a++) if (a == mv) { q[a] = qnew; vis[a] = vold + 1; }
+        *reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * mv) = qnew;
+        *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * mv) = (uint16_t)(vold + 1);
+        if (!last_rollout) {
+          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol);
+#pragma unroll
+          for (int c = 0; c < AP / 4; c++)
+            *reinterpret_cast<float4*>(nrec + Lay::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
+        }
+      }
+    }
+    return;
+  }
   int nindex = h.parent;
   int move = h.action;
   if (term) {
@@ -393,6 +545,30 @@ __global__ void __launch_bounds__(256) expand_backup_kernel(SearchParams P, int 
       value = fsub(1.f, value);                                                          // :324
     }
   }
+}
+
+template <class G, bool INJECT>
+__global__ void __launch_bounds__(256) expand_backup_kernel(SearchParams P, int L, int training, int last_rollout,
+                                                            const float* __restrict__ prior_in, const float* __restrict__ value_in, float cpuct) {
+  constexpr int W = Layout<G>::W;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  if (g >= L) return;
+  expand_backup_game<G, INJECT>(P, g, threadIdx.x & (W - 1), group_mask<W>(), training, last_rollout, prior_in, value_in, cpuct);
+}
+
+// One launch per rollout for the search side: expand + backUp of rollout k-1 (its network output is ready) followed at once by the
+// descent of rollout k.  The group that just walked a game's path back up re-descends through the same, still cached, records.
+template <class G>
+__global__ void __launch_bounds__(256, AG_MINBLOCKS) step_kernel(SearchParams P, int L, int rollout, int last_rollout, int training, float cpuct, u64 seed,
+                                                   u32 ply) {
+  constexpr int W = Layout<G>::W;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  if (g >= L) return;
+  const int l = threadIdx.x & (W - 1);
+  const unsigned gm = group_mask<W>();
+  expand_backup_game<G, false>(P, g, l, gm, training, 0, nullptr, nullptr, cpuct);
+  __syncwarp(gm);                                      // the group's global writes (q, visits, prior, flags) are ordered before its reads
+  select_game<G>(P, g, l, gm, L, rollout, last_rollout, cpuct, nullptr, seed, ply);
 }
 
 // ------------------------------------------------------------------------------------------------

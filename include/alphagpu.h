@@ -133,7 +133,8 @@ int agpu_get_leaves(agpu_ctx* ctx, int64_t L, int32_t* leaf /* 1-based node ids 
 /* actor on the current leaves (mcts_gpu.jl:414); results stay on the device, optionally copied out */
 int agpu_eval(agpu_ctx* ctx, int64_t L, int32_t slot, float* logits /* [L][A] or NULL */, float* value /* [L] or NULL */);
 /* softmax! + expand + backUp (mcts_gpu.jl:417-431).  prior/value NULL = use agpu_eval's device result
- * (softmax applied here); non-NULL prior[L][A] is taken as already softmaxed, as expand's input is. */
+ * (softmax applied here); non-NULL prior[L][A] is taken as already softmaxed, as expand's input is.
+ * (Where the engine re-solves the regularised policy during the backup it uses the cpuct of the preceding agpu_select.) */
 int agpu_expand_backup(agpu_ctx* ctx, int64_t L, int32_t training, int32_t last_rollout, const float* prior, const float* value);
 
 /* Tree tables for parity checks, layout-neutral: all [game][node]([action]); ids 1-based, 0 = none.

@@ -607,6 +607,7 @@ struct Tree {
   std::vector<float> nn_v;      // (L)
   // counters (reported by the bench: mean descent depth d̄, Newton iterations)
   int64_t cnt_descents, cnt_nodes_traversed, cnt_newton_solves, cnt_newton_iters;
+  int64_t max_newton_iters, max_depth, hist_iters[101];
 
   inline size_t i3(int a, int node, int64_t g) const { return (size_t)a + (size_t)s.A * ((size_t)node + (size_t)R * (size_t)g); }
   inline size_t i2(int node, int64_t g) const { return (size_t)node + (size_t)R * (size_t)g; }
@@ -628,6 +629,7 @@ static Tree* tree_create(const Spec& s, int R, int64_t L) {
   t->uid.resize(L); for (int64_t g = 0; g < L; g++) t->uid[g] = (uint32_t)g;
   t->nn_prior.assign((size_t)s.A * L, 0.f); t->nn_v.assign(L, 0.f);
   t->cnt_descents = t->cnt_nodes_traversed = t->cnt_newton_solves = t->cnt_newton_iters = 0;
+  t->max_newton_iters = t->max_depth = 0; memset(t->hist_iters, 0, sizeof(t->hist_iters));
   return t;
 }
 
@@ -687,8 +689,9 @@ static void descend_one(Tree* t, int64_t i, float cpuct, ProbFn prob, int64_t* n
       }
       float err = INFINITY, newerr = INFINITY;
       (*n_solve)++;
+      int iters_here = 0;
       for (int j = 1; j <= 100; j++) {                                // :141-162
-        (*n_iter)++;
+        (*n_iter)++; iters_here++;
         float S = prior_rem / alpha;
         float g = -prior_rem / (alpha * alpha);
         for (int k = 0; k < childnbr; k++) {
@@ -704,6 +707,8 @@ static void descend_one(Tree* t, int64_t i, float cpuct, ProbFn prob, int64_t* n
         alpha -= newerr / g;
         err = newerr;
       }
+      if (iters_here > t->max_newton_iters) t->max_newton_iters = iters_here;   // (racy under OpenMP; diagnostics only)
+      t->hist_iters[iters_here]++;
       for (int k = 0; k < A; k++) policy[k] = lambda * prior[k] / (alpha - q[k]);   // :165-169
     }
     float u = prob(cpt);
@@ -728,6 +733,7 @@ static void descend_one(Tree* t, int64_t i, float cpuct, ProbFn prob, int64_t* n
     nindex = t->childID[t->ic(Achild[bestmove - 1] - 1, nindex - 1, i)];   // :192
     cpt += 1;
   }
+  if (cpt - 1 > t->max_depth) t->max_depth = cpt - 1;
   t->leaf[i] = nindex;                                                // :195
 }
 
@@ -1099,6 +1105,9 @@ int orc_tree_poke(void* tp, int64_t g, int node, const float* prior, const float
   }
   t->expanded[t->i2(node - 1, g)] = 1; t->uptodate[t->i2(node - 1, g)] = 0;
   return 0;
+}
+int orc_get_extremes(void* tp, int64_t* out /* [2 + 101] */) {
+  Tree* t = (Tree*)tp; out[0] = t->max_newton_iters; out[1] = t->max_depth; for (int i = 0; i <= 100; i++) out[2 + i] = t->hist_iters[i]; return 0;
 }
 int orc_get_counters(void* tp, int64_t* out4) {
   Tree* t = (Tree*)tp; out4[0] = t->cnt_descents; out4[1] = t->cnt_nodes_traversed; out4[2] = t->cnt_newton_solves; out4[3] = t->cnt_newton_iters; return 0;
