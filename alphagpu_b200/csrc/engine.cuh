@@ -3,6 +3,8 @@
 // game plugin is instantiated in engine_*.cu.
 #pragma once
 #include <cstdio>
+#include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -116,6 +118,18 @@ struct EngineT : EngineBase {
   DevBuf<int8_t> s_state, s_player, s_fstate;
   DevBuf<float> s_policy, s_value;
   DevBuf<int32_t> s_game, s_ply;
+  // segmented graph replay of the rollout loop: the live games are cut into `nseg` independent slices, each replays the whole
+  // R-rollout loop from a CUDA graph on its own stream, so that one slice's network chain overlaps another slice's descents
+  // and the per-launch latency floor is shared instead of paid serially.
+  static constexpr int MAX_SEG = 8;
+  int nseg = 4;
+  cudaStream_t seg_stream[MAX_SEG] = {};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_SEG] = {};
+  SegParams* seg_host = nullptr;              // pinned [MAX_SEG]
+  DevBuf<SegParams> seg_dev;
+  int64_t seg_cap = 0;                        // slots a slice's graph is sized for
+  struct GraphSet { int visits, slot, training; std::vector<cudaGraphExec_t> exec; };
+  std::vector<GraphSet> graphs;
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -126,6 +140,11 @@ struct EngineT : EngineBase {
 
   ~EngineT() override {
     if (stream) cudaStreamSynchronize(stream);
+    drop_graphs();
+    for (int i = 0; i < MAX_SEG; i++) { if (seg_stream[i]) cudaStreamDestroy(seg_stream[i]); if (ev_join[i]) cudaEventDestroy(ev_join[i]); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (seg_host) cudaFreeHost(seg_host);
+    seg_dev.release();
     for (auto& e : ev_pending) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     for (auto& e : ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     path_node.release(); path_move.release(); path_len.release(); tree.release(); nnodes.release(); leaf.release(); block_count.release(); total_dev.release(); uid.release(); uid_b.release();
@@ -202,8 +221,22 @@ struct EngineT : EngineBase {
     P.tree = tree.p; P.game_stride = (size_t)R * Lay::REC; P.R = R; P.nnodes = nnodes.p; P.leaf = leaf.p; P.uid = uid.p;
     P.policy_final = policy_final.p; P.nn_out = nn_out.p; P.counters = nullptr;
     P.path_node = path_node.p; P.path_move = path_move.p; P.path_len = path_len.p;
+    if (const char* e = getenv("AGPU_SEGMENTS")) nseg = atoi(e);
+    if (nseg < 1) nseg = 1;
+    if (nseg > MAX_SEG) nseg = MAX_SEG;
+    for (int i = 0; i < nseg; i++) { AG_CK(cudaStreamCreateWithFlags(&seg_stream[i], cudaStreamNonBlocking)); AG_CK(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming)); }
+    AG_CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    AG_CK(cudaMallocHost((void**)&seg_host, sizeof(SegParams) * MAX_SEG));
+    AG_CK(seg_dev.ensure(MAX_SEG));
+    seg_cap = ((L_cap + nseg - 1) / nseg + 255) / 256 * 256;
+    if (is_tc()) AG_CK(tc_init());
     AG_CK(cudaStreamSynchronize(stream));
     return AGPU_OK;
+  }
+
+  void drop_graphs() {
+    for (auto& gs : graphs) for (auto e : gs.exec) if (e) cudaGraphExecDestroy(e);
+    graphs.clear();
   }
 
   bool is_tc() const { return cfg.nn_mode == AGPU_NN_BF16_TC || cfg.nn_mode == AGPU_NN_FP16_TC; }
@@ -213,7 +246,7 @@ struct EngineT : EngineBase {
 
   NNInput nn_input_tree() const {
     NNInput I; I.tree = tree.p; I.game_stride = P.game_stride; I.rec = Lay::REC; I.off_state = Lay::OFF_STATE; I.nc = G::Geo::NC; I.VS = G::VS;
-    I.leaf = leaf.p; I.x_direct = nullptr;
+    I.leaf = leaf.p; I.x_direct = nullptr; I.seg = nullptr;
     return I;
   }
 
@@ -225,6 +258,8 @@ struct EngineT : EngineBase {
     NetSlot& s = nets[slot];
     const int in = 2 * G::VS, n = cfg.width, k = cfg.blocks;
     AG_CK(cudaSetDevice(cfg.device));
+    const NetDev before = s.dev;
+    const bool was_set = s.set;
     AG_CK(s.base.ensure((size_t)n * in)); AG_CK(s.res.ensure((size_t)std::max(1, k) * n * n)); AG_CK(s.pol_w.ensure((size_t)A * n));
     AG_CK(s.pol_b.ensure(A)); AG_CK(s.val_w.ensure(n)); AG_CK(s.val_b.ensure(1));
     AG_CK(cudaMemcpyAsync(s.base.p, base, sizeof(float) * n * in, cudaMemcpyHostToDevice, stream));
@@ -252,21 +287,82 @@ struct EngineT : EngineBase {
     }
     AG_CK(cudaStreamSynchronize(stream));
     s.set = true;
+    if (!was_set || memcmp(&before, &s.dev, sizeof(NetDev)) != 0) drop_graphs();   // graphs bake the weight pointers
     return AGPU_OK;
   }
 
-  int run_nn(int slot, const NNInput& I, int64_t L, float* out, int outs) {
+  cudaError_t nn_on(cudaStream_t st, int slot, const NNInput& I, int64_t L, float* out, int outs) {
     const NetSlot& s = nets[slot];
-    if (is_tc()) {
-      cudaError_t e = cudaSuccess;
-      launch(K_NN, [&] { e = tc_forward(s.dev, I, (int)L, out, outs, stream, tc_fmt()); });
-      AG_CK(e);
-    } else {
-      constexpr int GT = 8;
-      const size_t smem = sizeof(float) * GT * (s.dev.in + s.dev.n);
-      launch(K_NN, [&] { nn_fp32_kernel<GT><<<(int)((L + GT - 1) / GT), s.dev.n, smem, stream>>>(s.dev, I, (int)L, out, outs); });
-      AG_CK(cudaGetLastError());
+    if (is_tc()) return tc_forward(s.dev, I, (int)L, out, outs, st, tc_fmt());
+    constexpr int GT = 8;
+    const size_t smem = sizeof(float) * GT * (s.dev.in + s.dev.n);
+    nn_fp32_kernel<GT><<<(int)((L + GT - 1) / GT), s.dev.n, smem, st>>>(s.dev, I, (int)L, out, outs);
+    return cudaGetLastError();
+  }
+  int run_nn(int slot, const NNInput& I, int64_t L, float* out, int outs) {
+    cudaError_t e = cudaSuccess;
+    launch(K_NN, [&] { e = nn_on(stream, slot, I, L, out, outs); });
+    AG_CK(e);
+    return AGPU_OK;
+  }
+
+  // ---- segmented graph replay ----
+  // records the rollout loop of slice i (capacity seg_cap slots) on its stream and instantiates it
+  int build_graph(int i, int visits, int slot, cudaGraphExec_t* out) {
+    cudaStream_t st = seg_stream[i];
+    const SegParams* sp = seg_dev.p + i;
+    NNInput I = nn_input_tree();
+    I.seg = reinterpret_cast<const int*>(sp);
+    const int gb = blocks_for_groups(seg_cap);
+    AG_CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    cudaError_t e = cudaSuccess;
+    for (int k = 0; k < visits && e == cudaSuccess; k++) {
+      const int last = (k == visits - 1);
+      if (k == 0) select_seg_kernel<G><<<gb, 256, 0, st>>>(P, sp, 0, last);
+      else step_seg_kernel<G><<<gb, 256, 0, st>>>(P, sp, k, last);
+      e = nn_on(st, slot, I, seg_cap, nn_out.p, Lay::OUTS);
+      if (last) expand_seg_kernel<G><<<gb, 256, 0, st>>>(P, sp, 1);
     }
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = cudaStreamEndCapture(st, &graph);
+    AG_CK(e);
+    AG_CK(e2);
+    AG_CK(cudaGraphInstantiate(out, graph, 0));
+    AG_CK(cudaGraphDestroy(graph));
+    return AGPU_OK;
+  }
+
+  // enqueues one mcts_single over L live games as nseg concurrent slices; returns with the main stream ordered after all of them
+  int enqueue_search_segmented(int64_t L, int slot, int visits, int training, float cpuct, uint64_t seed, uint32_t ply) {
+    GraphSet* gs = nullptr;
+    for (auto& g : graphs) if (g.visits == visits && g.slot == slot && g.training == training) gs = &g;
+    if (!gs) {
+      GraphSet n; n.visits = visits; n.slot = slot; n.training = training; n.exec.assign(nseg, nullptr);
+      for (int i = 0; i < nseg; i++) { int rc = build_graph(i, visits, slot, &n.exec[i]); if (rc != AGPU_OK) return rc; }
+      graphs.push_back(n);
+      gs = &graphs.back();
+    }
+    int64_t per = ((L + nseg - 1) / nseg + 255) / 256 * 256;        // tile-aligned slices
+    if (per > seg_cap) per = seg_cap;
+    int used = 0;
+    for (int i = 0; i < nseg; i++) {
+      const int64_t off = (int64_t)i * per;
+      const int64_t len = off >= L ? 0 : std::min<int64_t>(per, L - off);
+      SegParams& S = seg_host[i];
+      S.off = (int)off; S.len = (int)len; S.ply = ply; S.training = training; S.seed = seed; S.cpuct = cpuct; S.pad = 0;
+      if (len > 0) used = i + 1;
+    }
+    AG_CK(cudaMemcpyAsync(seg_dev.p, seg_host, sizeof(SegParams) * nseg, cudaMemcpyHostToDevice, stream));
+    AG_CK(cudaEventRecord(ev_fork, stream));
+    for (int i = 0; i < used; i++) {
+      AG_CK(cudaStreamWaitEvent(seg_stream[i], ev_fork, 0));
+      AG_CK(cudaGraphLaunch(gs->exec[i], seg_stream[i]));
+      AG_CK(cudaEventRecord(ev_join[i], seg_stream[i]));
+      AG_CK(cudaStreamWaitEvent(stream, ev_join[i], 0));
+      launch_count += 2 * visits + 1;
+      kt.launches[K_SELECT] += visits; kt.launches[K_NN] += visits; kt.launches[K_EXPAND] += 1;
+    }
+    last_cpuct = cpuct;
     return AGPU_OK;
   }
 
@@ -417,7 +513,8 @@ struct EngineT : EngineBase {
     int rc = upload_prob(prob, L, visits, &dprob);
     if (rc != AGPU_OK) return rc;
     launch(K_BEGIN, [&] { root_reset_kernel<G><<<blocks_for_threads(L), 256, 0, stream>>>(P, (int)L, nullptr, nullptr); });
-    rc = enqueue_search(L, slot, visits, training, cpuct, dprob, seed, ply);
+    rc = (dprob || profiling || nseg <= 1) ? enqueue_search(L, slot, visits, training, cpuct, dprob, seed, ply)
+                                           : enqueue_search_segmented(L, slot, visits, training, cpuct, seed, ply);
     if (rc != AGPU_OK) return rc;
     AG_CK(cudaStreamSynchronize(stream));
     if (profiling) harvest();
@@ -592,9 +689,14 @@ struct EngineT : EngineBase {
     L_live = ngames;
     int64_t L = ngames, sims = 0, npos = 0, count = 0;
     uint32_t round = 0;
+    const bool trace_plies = getenv("AGPU_TRACE_PLIES") != nullptr;   // development: per-ply wall time on stderr
+    double t_prev = 0;
+    auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+    if (trace_plies) t_prev = now_ms();
     while (L > 0) {
       const int actor = duel ? ((round % 2 == 0) ? slot : slot_b) : slot;                  // :592-596
-      int rc = enqueue_search(L, actor, visits, duel ? 0 : 1, cpuct, nullptr, seed, round);   // mcts_single (:503, :599)
+      int rc = (profiling || nseg <= 1) ? enqueue_search(L, actor, visits, duel ? 0 : 1, cpuct, nullptr, seed, round)   // mcts_single (:503, :599)
+                                        : enqueue_search_segmented(L, actor, visits, duel ? 0 : 1, cpuct, seed, round);
       if (rc != AGPU_OK) return rc;
       sims += L * visits; npos += L;
       const int nb = blocks_for_threads(L);
@@ -604,6 +706,7 @@ struct EngineT : EngineBase {
       launch(K_COMPACT, [&] { compact_kernel<G><<<nb, 256, 0, stream>>>(P, (int)L, Y, st_b.p, uid_b.p); });
       AG_CK(cudaMemcpyAsync(total_host, total_dev.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
       AG_CK(cudaStreamSynchronize(stream));                                                  // one host sync per ply (the reference: 6·R+3)
+      if (trace_plies) { const double t = now_ms(); fprintf(stderr, "ply %u L %lld ms %.3f us/rollout %.2f\n", round, (long long)L, t - t_prev, 1e3 * (t - t_prev) / visits); t_prev = t; }
       count += L;
       L = *total_host;
       round += 1;

@@ -35,6 +35,7 @@ struct NNInput {
   int VS;
   const int32_t* leaf;     // [L] 0-based node per game
   const float* x_direct;   // [L][2VS] already encoded (agpu_forward)
+  const int* seg;          // optional {off, len} in device memory: evaluate slots [off, off+len) (graph replay); else [0, L)
 };
 
 AG_D bool nn_input_bit(const NNInput& I, int g, int j) {
@@ -51,7 +52,8 @@ __global__ void nn_fp32_kernel(NetDev net, NNInput I, int L, float* __restrict__
   const int n = net.n, in = net.in;
   float* xin = sm;             // [GT][in]
   float* b = sm + GT * in;     // [GT][n]
-  const int g0 = blockIdx.x * GT;
+  int g0 = blockIdx.x * GT;
+  if (I.seg) { const int off = I.seg[0], len = I.seg[1]; if (g0 >= len) return; L = off + len; g0 += off; }
   const int o = threadIdx.x;
   for (int t = o; t < GT * in; t += n) {
     const int gg = t / in, j = t % in, g = g0 + gg;
@@ -115,6 +117,7 @@ size_t tc_image_bytes(int in, int n, int k, int A);
 void tc_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
                     const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host, int fmt);
 cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt);
+cudaError_t tc_init();
 extern long long* g_tc_dbg;
 
 }  // namespace ag

@@ -148,6 +148,13 @@ struct TcArgs {
 
 template <int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNInput I, int L, float* __restrict__ out, int outs) {
+  int seg_off = 0;
+  if (I.seg) {                                     // graph replay: this launch covers slots [off, off+len); surplus CTAs leave at once
+    seg_off = I.seg[0];
+    const int len = I.seg[1];
+    if ((int)blockIdx.x * (TC_TILES * TC_TILE_M) >= len) return;
+    L = seg_off + len;
+  }
   extern __shared__ unsigned char smem_raw[];
   // 1024-byte alignment for the 128B swizzle atoms
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -195,7 +202,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
     const int wq = warp & 3;                       // TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31)
     const int ch = (warp >> 2) & 1;                // column half handled by this warp
     const int r = wq * 32 + lane;                  // row in tile == TMEM lane
-    const int g = blockIdx.x * (TC_TILES * TC_TILE_M) + t * TC_TILE_M + r;
+    const int g = seg_off + blockIdx.x * (TC_TILES * TC_TILE_M) + t * TC_TILE_M + r;
     unsigned char* At = sA + t * TC_A_BYTES;
     const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);                       // column offset of this tile
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ch * 64);   // lane base of this warp's quarter, its column half
@@ -437,14 +444,13 @@ void tc_build_image(const float* base, const float* const* res, const float* pol
 
 long long* g_tc_dbg = nullptr;   // development: set through agpu_debug_tc_trace
 
+cudaError_t tc_init() {
+  cudaError_t e = cudaFuncSetAttribute(tc_mlp128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  return e;
+}
+
 cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_mlp128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
   TcArgs T;
   T.img = (const unsigned char*)net.tc_img; T.bias = net.tc_bias; T.nlayers = net.k + 2; T.k0_steps = (net.in + 15) / 16; T.A = net.A;
   T.NH = head_n(net.A); T.in = net.in;

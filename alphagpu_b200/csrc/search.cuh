@@ -87,6 +87,17 @@ struct SearchParams {
   uint8_t* path_len;     // [L]
 };
 
+// One independent slice of the live games.  The rollout loop of a slice is replayed from a CUDA graph on its own stream, so
+// everything that changes from ply to ply is read from this device-resident record instead of being a kernel argument.
+struct SegParams {
+  int off, len;          // slots [off, off+len)
+  u32 ply;
+  int training;
+  u64 seed;
+  float cpuct;
+  int pad;
+};
+
 template <int W> AG_D unsigned group_mask() {
   return W == 32 ? 0xffffffffu : (((1u << W) - 1u) << ((threadIdx.x & 31) & ~(W - 1)));
 }
@@ -569,6 +580,36 @@ __global__ void __launch_bounds__(256, AG_MINBLOCKS) step_kernel(SearchParams P,
   expand_backup_game<G, false>(P, g, l, gm, training, 0, nullptr, nullptr, cpuct);
   __syncwarp(gm);                                      // the group's global writes (q, visits, prior, flags) are ordered before its reads
   select_game<G>(P, g, l, gm, L, rollout, last_rollout, cpuct, nullptr, seed, ply);
+}
+
+// ---- the same three launches, addressed through a SegParams record (graph replay, one stream per slice) ----
+template <class G>
+__global__ void __launch_bounds__(256, AG_MINBLOCKS) select_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
+  constexpr int W = Layout<G>::W;
+  const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  const SegParams S = *sp;
+  if (gl >= S.len) return;
+  select_game<G>(P, S.off + gl, threadIdx.x & (W - 1), group_mask<W>(), 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply);
+}
+template <class G>
+__global__ void __launch_bounds__(256, AG_MINBLOCKS) step_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
+  constexpr int W = Layout<G>::W;
+  const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  const SegParams S = *sp;
+  if (gl >= S.len) return;
+  const int g = S.off + gl, l = threadIdx.x & (W - 1);
+  const unsigned gm = group_mask<W>();
+  expand_backup_game<G, false>(P, g, l, gm, S.training, 0, nullptr, nullptr, S.cpuct);
+  __syncwarp(gm);
+  select_game<G>(P, g, l, gm, 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply);
+}
+template <class G>
+__global__ void __launch_bounds__(256) expand_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int last_rollout) {
+  constexpr int W = Layout<G>::W;
+  const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
+  const SegParams S = *sp;
+  if (gl >= S.len) return;
+  expand_backup_game<G, false>(P, S.off + gl, threadIdx.x & (W - 1), group_mask<W>(), S.training, last_rollout, nullptr, nullptr, S.cpuct);
 }
 
 // ------------------------------------------------------------------------------------------------
