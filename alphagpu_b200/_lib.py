@@ -15,7 +15,7 @@ OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_ILLEGAL_MOVE = 0, -1, -
 CONNECT4, GOBANG, HEX, REVERSI8, REVERSI6 = 0, 1, 2, 3, 4
 NN_BF16_TC, NN_FP32, NN_FP16_TC = 0, 1, 2
 NKERNELS = 8
-KERNEL_CLASSES = ("select", "nn", "expand_backup", "begin", "finish_ply", "compact", "finalize", "other")
+KERNEL_CLASSES = ("select", "nn", "expand_backup", "begin", "finish_ply", "compact", "finalize", "ply_fused")
 
 
 class Config(C.Structure):

@@ -12,6 +12,7 @@
 #include "../../include/alphagpu.h"
 #include "nn.cuh"
 #include "search.cuh"
+#include "fused.cuh"
 
 namespace ag {
 
@@ -130,6 +131,10 @@ struct EngineT : EngineBase {
   int64_t seg_cap = 0;                        // slots a slice's graph is sized for
   struct GraphSet { int visits, slot, training; std::vector<cudaGraphExec_t> exec; };
   std::vector<GraphSet> graphs;
+  // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
+  static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;
+  bool use_fused = false;
+  int num_sms = 148, fused_min_gpc = 32;
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -230,8 +235,46 @@ struct EngineT : EngineBase {
     AG_CK(seg_dev.ensure(MAX_SEG));
     seg_cap = ((L_cap + nseg - 1) / nseg + 255) / 256 * 256;
     if (is_tc()) AG_CK(tc_init());
+    if constexpr (FUSED_OK) {
+      if (is_tc()) {
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::F_SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::F_SMEM));
+        use_fused = true;
+        if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
+        if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
+        cudaDeviceProp prop;
+        AG_CK(cudaGetDeviceProperties(&prop, cfg.device));
+        num_sms = prop.multiProcessorCount;
+      }
+    }
     AG_CK(cudaStreamSynchronize(stream));
     return AGPU_OK;
+  }
+
+  // one launch for the whole rollout loop of a ply (fused.cuh)
+  int enqueue_search_fused(int64_t L, int slot, int visits, int training, float cpuct, uint64_t seed, uint32_t ply) {
+    if constexpr (FUSED_OK) {
+      const NetSlot& ns = nets[slot];
+      tc::TcArgs T;
+      T.img = (const unsigned char*)ns.dev.tc_img; T.bias = ns.dev.tc_bias; T.nlayers = ns.dev.k + 2; T.k0_steps = (ns.dev.in + 15) / 16;
+      T.A = ns.dev.A; T.NH = tc::head_n(ns.dev.A); T.in = ns.dev.in; T.dbg = nullptr;
+      SegParams S; S.off = 0; S.len = (int)L; S.ply = ply; S.training = training; S.seed = seed; S.cpuct = cpuct; S.pad = 0;
+      // games per CTA: spread the live games over all SMs (one CTA per SM), at least 32 and at most 256 per CTA
+      int gpc = (int)((L + num_sms - 1) / num_sms);
+      gpc = (gpc + 7) / 8 * 8;
+      if (gpc < fused_min_gpc) gpc = fused_min_gpc;
+      if (gpc > fused::F_GAMES) gpc = fused::F_GAMES;
+      const int grid = (int)((L + gpc - 1) / gpc);
+      if (tc_fmt() == 0) launch(K_OTHER, [&] { fused::ply_kernel<G, 0><<<grid, fused::F_THREADS, fused::F_SMEM, stream>>>(P, T, S, visits, gpc); });
+      else launch(K_OTHER, [&] { fused::ply_kernel<G, 1><<<grid, fused::F_THREADS, fused::F_SMEM, stream>>>(P, T, S, visits, gpc); });
+      AG_CK(cudaGetLastError());
+      last_cpuct = cpuct;
+      return AGPU_OK;
+    } else {
+      (void)L; (void)slot; (void)visits; (void)training; (void)cpuct; (void)seed; (void)ply;
+      err = "fused ply kernel not available for this game";
+      return AGPU_ERR_INVALID;
+    }
   }
 
   void drop_graphs() {
@@ -513,8 +556,9 @@ struct EngineT : EngineBase {
     int rc = upload_prob(prob, L, visits, &dprob);
     if (rc != AGPU_OK) return rc;
     launch(K_BEGIN, [&] { root_reset_kernel<G><<<blocks_for_threads(L), 256, 0, stream>>>(P, (int)L, nullptr, nullptr); });
-    rc = (dprob || profiling || nseg <= 1) ? enqueue_search(L, slot, visits, training, cpuct, dprob, seed, ply)
-                                           : enqueue_search_segmented(L, slot, visits, training, cpuct, seed, ply);
+    rc = (use_fused && !dprob) ? enqueue_search_fused(L, slot, visits, training, cpuct, seed, ply)
+         : (dprob || profiling || nseg <= 1) ? enqueue_search(L, slot, visits, training, cpuct, dprob, seed, ply)
+                                             : enqueue_search_segmented(L, slot, visits, training, cpuct, seed, ply);
     if (rc != AGPU_OK) return rc;
     AG_CK(cudaStreamSynchronize(stream));
     if (profiling) harvest();
@@ -695,8 +739,9 @@ struct EngineT : EngineBase {
     if (trace_plies) t_prev = now_ms();
     while (L > 0) {
       const int actor = duel ? ((round % 2 == 0) ? slot : slot_b) : slot;                  // :592-596
-      int rc = (profiling || nseg <= 1) ? enqueue_search(L, actor, visits, duel ? 0 : 1, cpuct, nullptr, seed, round)   // mcts_single (:503, :599)
-                                        : enqueue_search_segmented(L, actor, visits, duel ? 0 : 1, cpuct, seed, round);
+      int rc = use_fused ? enqueue_search_fused(L, actor, visits, duel ? 0 : 1, cpuct, seed, round)                     // mcts_single (:503, :599)
+               : (profiling || nseg <= 1) ? enqueue_search(L, actor, visits, duel ? 0 : 1, cpuct, nullptr, seed, round)
+                                          : enqueue_search_segmented(L, actor, visits, duel ? 0 : 1, cpuct, seed, round);
       if (rc != AGPU_OK) return rc;
       sims += L * visits; npos += L;
       const int nb = blocks_for_threads(L);

@@ -1,0 +1,248 @@
+// fused.cuh — one persistent kernel per ply: the whole R-rollout loop of mcts_single (mcts_gpu.jl:396-439) on chip.
+//
+// A CTA owns 256 games (two 128-row tiles) for the entire search of a ply and alternates, per rollout,
+//   search phase : all 1024 threads, 8 lanes per game, two passes of 128 games: expand+backUp of the previous rollout, then the
+//                  descent of this one (the same device functions as the stand-alone kernels, search.cuh);
+//   network phase: the tcgen05/TMEM chain of nn_tc.cu re-organised for 32 warps: warp w serves tile w/16, TMEM lane quarter w%4
+//                  and the 32-column slice (w/4)%4; one lane per tile issues the MMAs; the fp32 residual stream lives in TMEM
+//                  (columns 256..511) so the epilogue needs few registers; weights stream global->shared through the 3-stage
+//                  bulk-copy ring without ever draining between rollouts.
+// Games of a CTA depend on each other only through their shared GEMM tile, so there is no grid-wide barrier and no kernel
+// boundary inside a ply: the per-rollout cost is the on-chip critical path instead of three launches plus their tails
+// (profiles/r01_ply_trace_*.txt: 70 us -> per rollout at 32768 games, 25-40 us floor at small L with separate launches).
+#pragma once
+#include "search.cuh"
+#include "tc_ptx.cuh"
+
+namespace ag {
+
+namespace fused {
+using namespace tc;
+
+constexpr int F_THREADS = 1024;
+constexpr int F_GAMES = TC_TILES * TC_TILE_M;                          // 256 games per CTA
+constexpr int F_SMEM = TC_TILES * TC_A_BYTES + TC_STAGES * TC_W_STAGE_BYTES + 1024 + 1024;
+
+AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+        "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+AG_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <class G, int FMT>
+__global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+  typedef Layout<G> Lay;
+  constexpr int W = Lay::W;
+  static_assert(Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= TC_N, "fused ply kernel: small boards only");
+  // gpc = games per CTA (<= 256), chosen by the host so that the live games spread over all SMs: the search phase of a CTA is
+  // issue-bound on its one SM, so late plies run many lightly filled CTAs rather than a few full ones.
+  const int cta_first = (int)blockIdx.x * gpc;                         // first local slot of this CTA
+  if (cta_first >= S.len) return;
+  const int count = min(gpc, S.len - cta_first);                       // games of this CTA
+  const int L_end = S.off + cta_first + count;                         // one past this CTA's last slot
+  const int ntiles = count > TC_TILE_M ? 2 : 1;                        // a CTA with <= 128 games runs a single tile
+
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;                                            // [2][32 KB] activations (A operands)
+  unsigned char* sW = smem + TC_TILES * TC_A_BYTES;                    // [3][32 KB] weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + TC_STAGES * TC_W_STAGE_BYTES);
+  // bars[0..2] full, [3..5] empty, [6..7] mma_done, [8] stagger (one-shot)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  float* sbias = reinterpret_cast<float*>(bars + 10);                  // [128] head biases
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, ntiles); }
+    for (int t = 0; t < TC_TILES; t++) mbar_init(bar_done + 8 * t, 1);
+    mbar_init(bar_stagger, 1);
+    fence_barrier_init();
+  }
+  if (threadIdx.x < TC_N) sbias[threadIdx.x] = T.bias[threadIdx.x];
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);                 // 2 x 128 accumulator columns + 2 x 128 residual columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int nlayers = T.nlayers;
+  const int total_layers = visits * nlayers;
+  // weight image of global layer index wl (= rollout * nlayers + layer) -> ring stage wl % 3
+  auto load_layer = [&](int wl) {
+    const int s = wl % TC_STAGES, l = wl % nlayers;
+    const uint32_t bytes = (l == nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
+    if (wl >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((wl / TC_STAGES) - 1) & 1);
+    mbar_expect_tx(bar_full + 8 * s, bytes);
+    bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + (size_t)l * TC_W_STAGE_BYTES, bytes, bar_full + 8 * s);
+  };
+  if (threadIdx.x == 0) {
+    load_layer(0);
+    if (total_layers > 1) load_layer(1);
+  }
+
+  // ---- roles ----
+  // search: group of W lanes per game, pass p covers local games p*128 .. p*128+127
+  const int sg = threadIdx.x / W, sl = threadIdx.x & (W - 1);
+  const unsigned gm = group_mask<W>();
+  constexpr int GROUPS = F_THREADS / W;                                // games per pass
+  constexpr int PASSES = F_GAMES / GROUPS;
+  // network: tile, TMEM lane quarter, 32-column slice
+  const int t = warp >> 4, wq = warp & 3, cs = (warp >> 2) & 3;
+  const int r = wq * 32 + lane;
+  const int g_row = S.off + cta_first + t * TC_TILE_M + r;            // the game whose activations this thread carries
+  unsigned char* At = sA + t * TC_A_BYTES;
+  const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
+  const uint32_t tmem_res = tmem_base + (uint32_t)(256 + t * TC_N);
+  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
+  const bool issuer = (warp & 15) == 0 && lane == 0;
+  const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
+
+  int wl = 0;                                                          // global layer counter (ring / barrier phases)
+  for (int k = 0; k < visits; k++) {
+    const int last = (k == visits - 1);
+    // ================= search phase =================
+#pragma unroll 1
+    for (int p = 0; p < PASSES; p++) {
+      const int g = S.off + cta_first + p * GROUPS + sg;
+      if (g < L_end) {
+        if (k > 0) {
+          expand_backup_game<G, false>(P, g, sl, gm, S.training, 0, nullptr, nullptr, S.cpuct);
+          __syncwarp(gm);
+        }
+        select_game<G>(P, g, sl, gm, 0, k, last, S.cpuct, nullptr, S.seed, S.ply);
+      }
+    }
+    __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
+
+    // ================= network phase =================
+    {
+      // A operand of the base layer: this thread's 32 operand columns of its row (decoder, mcts_gpu.jl:202-223)
+      uint32_t bits = 0;
+      if (g_row < L_end) {
+        const u64* st = reinterpret_cast<const u64*>(P.tree + (size_t)g_row * P.game_stride + (size_t)P.leaf[g_row] * Lay::REC + Lay::OFF_STATE);
+        const u64 bp = st[0], bo = st[1];
+        constexpr int VS = G::VS;
+        const u64 x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
+        const u64 x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
+        bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
+      }
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t byte = (bits >> (8 * i)) & 0xFFu;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
+        const int c = 4 * cs + i;                                      // chunk of 8 operands in the row, 0..15
+        *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    if (t >= ntiles) { wl += nlayers; __syncthreads(); continue; }      // idle tile: rejoin at the end-of-rollout barrier
+    fence_proxy_async();
+    named_bar_sync(1 + t, 512);
+
+    for (int l = 0; l < nlayers; l++, wl++) {
+      const int s = wl % TC_STAGES;
+      const bool is_head = (l == nlayers - 1);
+      const int nl = is_head ? T.NH : TC_N;
+      if (issuer) {
+        mbar_wait(bar_full + 8 * s, (wl / TC_STAGES) & 1);
+        if (wl == 0 && t == 1) mbar_wait(bar_stagger, 0);              // tile 1 trails tile 0 by one MMA phase
+        tc_fence_after();
+        const uint64_t ad0 = umma_desc(smem_u32(At));
+        const uint64_t bd0 = umma_desc(smem_u32(sW + s * TC_W_STAGE_BYTES));
+        const uint32_t idesc = umma_idesc<FMT>(nl);
+        const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
+#pragma unroll
+        for (int ks = 0; ks < TC_N / 16; ks++) {
+          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+          umma_bf16(tmem_acc, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar_done + 8 * t);
+        umma_commit(bar_empty + 8 * s);
+        if (wl == 0 && t == 0) umma_commit(bar_stagger);
+        if (t == 0 && wl + 2 < total_layers) load_layer(wl + 2);
+      }
+      mbar_wait(bar_done + 8 * t, wl & 1);
+      tc_fence_after();
+
+      if (!is_head) {
+        // epilogue: b = relu(acc) (base) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b)
+        const bool keep = (l + 2 < nlayers);                            // the last trunk layer's residual is not read again
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          uint32_t va[16], vh[16];
+          tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
+          if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
+            const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
+            vh[e] = __float_as_uint(hv);
+          }
+          if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; c2++) {
+            const int c = 4 * cs + 2 * i + c2;
+            const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[8 * c2 + 0]), __uint_as_float(vh[8 * c2 + 1])),
+                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 2]), __uint_as_float(vh[8 * c2 + 3])),
+                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 4]), __uint_as_float(vh[8 * c2 + 5])),
+                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 6]), __uint_as_float(vh[8 * c2 + 7])));
+            *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
+          }
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1 + t, 512);
+      } else {
+        // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> nn_out (global, read by the next search phase)
+        float* o = P.nn_out + (size_t)g_row * Lay::OUTS;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int a0 = cs * 32 + i * 16;
+          if (a0 < T.NH) {                                              // warp-uniform
+            uint32_t v[16];
+            tmem_ld16(tmem_acc + lane_sel + 16 * i, v);
+            tmem_ld_wait();
+            float z[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) z[e] = __uint_as_float(v[e]) + sbias[a0 + e];
+            if (T.A >= a0 && T.A < a0 + 16) {
+#pragma unroll
+              for (int e = 0; e < 16; e++) if (a0 + e == T.A) z[e] = c_sigmoidf(z[e]);
+            }
+            if (g_row < L_end) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; q4++)
+                if (a0 + 4 * q4 < Lay::OUTS) *reinterpret_cast<float4*>(o + a0 + 4 * q4) = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+            }
+          }
+        }
+        tc_fence_before();
+      }
+    }
+    __syncthreads();                                                   // nn_out (global) visible to the search phase
+  }
+
+  // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)
+#pragma unroll 1
+  for (int p = 0; p < PASSES; p++) {
+    const int g = S.off + cta_first + p * GROUPS + sg;
+    if (g < L_end) expand_backup_game<G, false>(P, g, sl, gm, S.training, 1, nullptr, nullptr, S.cpuct);
+  }
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fused
+}  // namespace ag

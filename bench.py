@@ -218,17 +218,26 @@ def main():
     per_sim = algorithmic_bytes_per_sim(spec.maxActions, S, dbar)
     classes = {k: v for k, v in kt.items() if isinstance(v, dict) and v["launches"]}
     total_ms = sum(v["ms"] for v in classes.values())
-    dom = max(("select", "expand_backup"), key=lambda k: classes[k]["ms"])
-    dom_ms = classes[dom]["ms"]
-    achieved = per_sim[dom] * pst["sims"] / (dom_ms * 1e-3) / 1e9
+    f_sim = 2 * (2 * spec.VectorizedState * WIDTH + BLOCKS * WIDTH * WIDTH + WIDTH * (spec.maxActions + 1))
+    fused = "ply_fused" in classes and classes["ply_fused"]["ms"] > 0.5 * total_ms
+    if fused:
+        # one persistent kernel per ply runs the whole rollout loop (search phases + tcgen05 chain): both rooflines refer to its duration
+        dom, dom_ms = "ply_fused", classes["ply_fused"]["ms"]
+        bytes_sim = per_sim["select"] + per_sim["expand_backup"] + per_sim["nn"]
+        nn_ms, nn_name = dom_ms, "ply_fused (tcgen05 chain inside the per-ply kernel)"
+    else:
+        dom = max(("select", "expand_backup"), key=lambda k: classes.get(k, {"ms": 0})["ms"])
+        dom_ms = classes[dom]["ms"]
+        bytes_sim = per_sim[dom] + (per_sim["expand_backup"] if dom == "select" else 0)   # the step kernel fuses expand+backup into select
+        nn_ms, nn_name = classes["nn"]["ms"], "nn (tcgen05 chain)"
+    achieved = bytes_sim * pst["sims"] / (dom_ms * 1e-3) / 1e9
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
             traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
     except Exception:
         pass
-    f_sim = 2 * (2 * spec.VectorizedState * WIDTH + BLOCKS * WIDTH * WIDTH + WIDTH * (spec.maxActions + 1))
-    nn_tf = f_sim * pst["sims"] / (classes["nn"]["ms"] * 1e-3) / 1e12
+    nn_tf = f_sim * pst["sims"] / (nn_ms * 1e-3) / 1e12
 
     line = {
         "metric": METRIC, "value": sims / (dev_ms * 1e-3), "unit": "sims/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -244,11 +253,12 @@ def main():
                 "ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": launches,
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
-                     "peak_source": peak_src, "bytes_per_sim": per_sim[dom], "avg_launch_us": 1e3 * dom_ms / classes[dom]["launches"],
-                     "share_of_step": dom_ms / total_ms,
-                     "note": "issue/latency-bound, not HBM-bound: see profiles/ (DRAM throughput 3% of peak, issue slots 50% busy)"},
-        "roofline_nn": {"kernel": "nn (tcgen05 chain)", "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
-                        "flop_per_sim": f_sim, "avg_launch_us": 1e3 * classes["nn"]["ms"] / classes["nn"]["launches"], "share_of_step": classes["nn"]["ms"] / total_ms},
+                     "peak_source": peak_src, "bytes_per_sim": bytes_sim, "avg_launch_us": 1e3 * dom_ms / classes[dom]["launches"],
+                     "share_of_step": dom_ms / total_ms, "sims_per_launch": pst["sims"] / classes[dom]["launches"],
+                     "note": "issue/latency-bound, not HBM-bound: see DESIGN.md §6 and profiles/ (DRAM throughput ~10% of peak, issue slots ~50% busy, "
+                             "41% of lanes active; the per-rollout dependent chain sets a floor independent of the number of live games)"},
+        "roofline_nn": {"kernel": nn_name, "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
+                        "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
     }
 

@@ -195,7 +195,7 @@ int agpu_duel(agpu_ctx* ctx, int32_t slot_a, int32_t slot_b, int32_t visits, int
 typedef struct agpu_kernel_times {
   /* per kernel class: launches and summed CUDA-event milliseconds since the last reset, measured on
    * the library's own stream when profiling is enabled.  Classes: 0 select 1 nn 2 expand_backup
-   * 3 begin/reinit 4 finish_ply 5 compact 6 finalize 7 other */
+   * 3 begin/reinit 4 finish_ply 5 compact 6 finalize 7 fused per-ply kernel (whole rollout loop) and misc */
   int64_t launches[AGPU_NKERNELS];
   double ms[AGPU_NKERNELS];
   int64_t nodes_traversed;   /* expanded nodes visited by descents (for d-bar), when profiling */

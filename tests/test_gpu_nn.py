@@ -124,3 +124,27 @@ def test_tc_selfplay_properties_full_size():
     res2, st2, smp2 = ctx.selfplay(R, games, cpuct=1.5, seed=1, want_samples=True)
     assert np.array_equal(res, res2) and all(np.array_equal(smp[k], smp2[k]) for k in smp)
     ctx.close()
+
+
+def test_fused_ply_kernel_equals_separate_kernels(monkeypatch):
+    """The persistent per-ply kernel (fused.cuh) and the per-rollout kernels (search.cuh + nn_tc.cu) run the same device functions
+    and the same MMA sequence: a whole self-play generation must come out identical, bit for bit."""
+    name = "connect4"
+    pnet, _ = make_nets(GAME_SPECS[name], 128, 6, seed=11)
+    games, R = 3000, 24          # not a multiple of 256: exercises partially filled tiles and CTAs
+    outs = []
+    for fused in ("1", "0"):
+        monkeypatch.setenv("AGPU_FUSED", fused)
+        ctx = ctx_for(name, R, games, 128, 6, nn_mode=2)
+        ctx.set_weights(pnet)
+        res, st, smp = ctx.selfplay(R, games, cpuct=1.5, seed=21)
+        outs.append((res, st, smp))
+        ctx.close()
+    (r1, s1, a), (r0, s0, b) = outs
+    assert np.array_equal(r1, r0) and s1["positions"] == s0["positions"] and s1["faults"] == 0
+    assert s1["kernel_launches"] < s0["kernel_launches"] / 10
+    for k in a:
+        if a[k].dtype.kind == "f":
+            assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+        else:
+            assert np.array_equal(a[k], b[k]), k
