@@ -148,7 +148,7 @@ def main():
     net = ag.ressimplesf(2 * spec.VectorizedState, spec.maxActions, WIDTH, BLOCKS, seed=0)
     ctx = ag.Context(spec, ROLLOUT, GAMES, WIDTH, BLOCKS, device=local_rank, nn_mode=args.nn_mode)
     ctx.set_weights(net)
-    uid_base = rank * GAMES
+    uid_base = rank * GAMES                                                      # weak scaling: every rank plays its own 32768 games
 
     def sync():
         torch.cuda.synchronize()
@@ -200,13 +200,10 @@ def main():
     ctx.close()
 
     # ---- reduce over ranks: time = max, work = sum ----
-    if world > 1:
-        t = torch.tensor([dev_ms, wall, e2e_wall], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        w = torch.tensor([sims, positions, launches, e2e_sims, d2h, h2d], dtype=torch.float64, device="cuda")
-        dist.all_reduce(w, op=dist.ReduceOp.SUM)
-        dev_ms, wall, e2e_wall = [float(x) for x in t.tolist()]
-        sims, positions, launches, e2e_sims, d2h, h2d = [int(x) for x in w.tolist()]
+    from alphagpu_b200 import parallel
+    (dev_ms, wall, e2e_wall), w = parallel.reduce_max_sum([dev_ms, wall, e2e_wall], [sims, positions, launches, e2e_sims, d2h, h2d],
+                                                          device="cuda" if world > 1 else None)
+    sims, positions, launches, e2e_sims, d2h, h2d = [int(x) for x in w]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
