@@ -134,7 +134,7 @@ struct EngineT : EngineBase {
   // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
   static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;
   bool use_fused = false;
-  int num_sms = 148, fused_min_gpc = 32;
+  int num_sms = 148, fused_min_gpc = 32, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -237,8 +237,11 @@ struct EngineT : EngineBase {
     if (is_tc()) AG_CK(tc_init());
     if constexpr (FUSED_OK) {
       if (is_tc()) {
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::F_SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::F_SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));
+        if (const char* e = getenv("AGPU_FUSED_TILES")) fused_tiles = atoi(e) == 2 ? 2 : 1;
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
@@ -259,14 +262,24 @@ struct EngineT : EngineBase {
       T.img = (const unsigned char*)ns.dev.tc_img; T.bias = ns.dev.tc_bias; T.nlayers = ns.dev.k + 2; T.k0_steps = (ns.dev.in + 15) / 16;
       T.A = ns.dev.A; T.NH = tc::head_n(ns.dev.A); T.in = ns.dev.in; T.dbg = nullptr;
       SegParams S; S.off = 0; S.len = (int)L; S.ply = ply; S.training = training; S.seed = seed; S.cpuct = cpuct; S.pad = 0;
-      // games per CTA: spread the live games over all SMs (one CTA per SM), at least 32 and at most 256 per CTA
-      int gpc = (int)((L + num_sms - 1) / num_sms);
+      // games per CTA: spread the live games over all CTA slots of the chip (2 per SM with one tile per CTA), at least
+      // fused_min_gpc and at most 128 per tile
+      const int slots = num_sms * (fused_tiles == 1 ? 2 : 1), cap = 128 * fused_tiles;
+      int gpc = (int)((L + slots - 1) / slots);
       gpc = (gpc + 7) / 8 * 8;
       if (gpc < fused_min_gpc) gpc = fused_min_gpc;
-      if (gpc > fused::F_GAMES) gpc = fused::F_GAMES;
+      if (gpc > cap) gpc = cap;
       const int grid = (int)((L + gpc - 1) / gpc);
-      if (tc_fmt() == 0) launch(K_OTHER, [&] { fused::ply_kernel<G, 0><<<grid, fused::F_THREADS, fused::F_SMEM, stream>>>(P, T, S, visits, gpc); });
-      else launch(K_OTHER, [&] { fused::ply_kernel<G, 1><<<grid, fused::F_THREADS, fused::F_SMEM, stream>>>(P, T, S, visits, gpc); });
+      const int fmt = tc_fmt();
+      launch(K_OTHER, [&] {
+        if (fused_tiles == 1) {
+          if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
+        } else {
+          if (fmt == 0) fused::ply_kernel<G, 0, 2><<<grid, fused::FCfg<2>::THREADS, fused::FCfg<2>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 2><<<grid, fused::FCfg<2>::THREADS, fused::FCfg<2>::SMEM, stream>>>(P, T, S, visits, gpc);
+        }
+      });
       AG_CK(cudaGetLastError());
       last_cpuct = cpuct;
       return AGPU_OK;

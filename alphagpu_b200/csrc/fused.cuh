@@ -19,9 +19,17 @@ namespace ag {
 namespace fused {
 using namespace tc;
 
-constexpr int F_THREADS = 1024;
-constexpr int F_GAMES = TC_TILES * TC_TILE_M;                          // 256 games per CTA
-constexpr int F_SMEM = TC_TILES * TC_A_BYTES + TC_STAGES * TC_W_STAGE_BYTES + 1024 + 1024;
+// NT = tiles per CTA.  NT = 2: 1024 threads, one CTA per SM, 3-stage weight ring.  NT = 1: 512 threads, 2-stage ring, TWO CTAs per
+// SM (98 KB shared memory, 256 TMEM columns, 64 registers each): while one CTA waits on its MMA chain the other's search phase
+// uses the issue slots.
+template <int NT> struct FCfg {
+  static constexpr int THREADS = 512 * NT;
+  static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
+  static constexpr int STAGES = NT == 1 ? 2 : 3;
+  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 1024;
+  static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
+  static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
+};
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -32,10 +40,12 @@ AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
 }
 AG_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <class G, int FMT>
-__global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+template <class G, int FMT, int NT>
+__global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   typedef Layout<G> Lay;
+  typedef FCfg<NT> C;
   constexpr int W = Lay::W;
+  constexpr int STAGES = C::STAGES;
   static_assert(Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= TC_N, "fused ply kernel: small boards only");
   // gpc = games per CTA (<= 256), chosen by the host so that the live games spread over all SMs: the search phase of a CTA is
   // issue-bound on its one SM, so late plies run many lightly filled CTAs rather than a few full ones.
@@ -43,13 +53,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArg
   if (cta_first >= S.len) return;
   const int count = min(gpc, S.len - cta_first);                       // games of this CTA
   const int L_end = S.off + cta_first + count;                         // one past this CTA's last slot
-  const int ntiles = count > TC_TILE_M ? 2 : 1;                        // a CTA with <= 128 games runs a single tile
+  const int ntiles = (NT == 2 && count > TC_TILE_M) ? 2 : 1;           // a CTA with <= 128 games runs a single tile
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = smem;                                            // [2][32 KB] activations (A operands)
-  unsigned char* sW = smem + TC_TILES * TC_A_BYTES;                    // [3][32 KB] weight ring
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + TC_STAGES * TC_W_STAGE_BYTES);
+  unsigned char* sW = smem + NT * TC_A_BYTES;                          // [STAGES][32 KB] weight ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * TC_W_STAGE_BYTES);
   // bars[0..2] full, [3..5] empty, [6..7] mma_done, [8] stagger (one-shot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   float* sbias = reinterpret_cast<float*>(bars + 10);                  // [128] head biases
@@ -58,13 +68,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArg
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, ntiles); }
-    for (int t = 0; t < TC_TILES; t++) mbar_init(bar_done + 8 * t, 1);
+    for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, ntiles); }
+    for (int t = 0; t < NT; t++) mbar_init(bar_done + 8 * t, 1);
     mbar_init(bar_stagger, 1);
     fence_barrier_init();
   }
   if (threadIdx.x < TC_N) sbias[threadIdx.x] = T.bias[threadIdx.x];
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);                 // 2 x 128 accumulator columns + 2 x 128 residual columns
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);        // NT x 128 accumulator columns + NT x 128 residual columns
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -74,30 +84,30 @@ __global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArg
   const int total_layers = visits * nlayers;
   // weight image of global layer index wl (= rollout * nlayers + layer) -> ring stage wl % 3
   auto load_layer = [&](int wl) {
-    const int s = wl % TC_STAGES, l = wl % nlayers;
+    const int s = wl % STAGES, l = wl % nlayers;
     const uint32_t bytes = (l == nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
-    if (wl >= TC_STAGES) mbar_wait(bar_empty + 8 * s, ((wl / TC_STAGES) - 1) & 1);
+    if (wl >= STAGES) mbar_wait(bar_empty + 8 * s, ((wl / STAGES) - 1) & 1);
     mbar_expect_tx(bar_full + 8 * s, bytes);
     bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + (size_t)l * TC_W_STAGE_BYTES, bytes, bar_full + 8 * s);
   };
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) {                                              // fill the ring: STAGES - 1 layers ahead
     load_layer(0);
-    if (total_layers > 1) load_layer(1);
+    if (STAGES > 2 && total_layers > 1) load_layer(1);
   }
 
   // ---- roles ----
   // search: group of W lanes per game, pass p covers local games p*128 .. p*128+127
   const int sg = threadIdx.x / W, sl = threadIdx.x & (W - 1);
   const unsigned gm = group_mask<W>();
-  constexpr int GROUPS = F_THREADS / W;                                // games per pass
-  constexpr int PASSES = F_GAMES / GROUPS;
+  constexpr int GROUPS = C::THREADS / W;                               // games per pass
+  constexpr int PASSES = C::GAMES / GROUPS;
   // network: tile, TMEM lane quarter, 32-column slice
   const int t = warp >> 4, wq = warp & 3, cs = (warp >> 2) & 3;
   const int r = wq * 32 + lane;
   const int g_row = S.off + cta_first + t * TC_TILE_M + r;            // the game whose activations this thread carries
   unsigned char* At = sA + t * TC_A_BYTES;
   const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
-  const uint32_t tmem_res = tmem_base + (uint32_t)(256 + t * TC_N);
+  const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
   const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
   const bool issuer = (warp & 15) == 0 && lane == 0;
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
@@ -146,11 +156,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArg
     named_bar_sync(1 + t, 512);
 
     for (int l = 0; l < nlayers; l++, wl++) {
-      const int s = wl % TC_STAGES;
+      const int s = wl % STAGES;
       const bool is_head = (l == nlayers - 1);
       const int nl = is_head ? T.NH : TC_N;
       if (issuer) {
-        mbar_wait(bar_full + 8 * s, (wl / TC_STAGES) & 1);
+        mbar_wait(bar_full + 8 * s, (wl / STAGES) & 1);
         if (wl == 0 && t == 1) mbar_wait(bar_stagger, 0);              // tile 1 trails tile 0 by one MMA phase
         tc_fence_after();
         const uint64_t ad0 = umma_desc(smem_u32(At));
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArg
         umma_commit(bar_done + 8 * t);
         umma_commit(bar_empty + 8 * s);
         if (wl == 0 && t == 0) umma_commit(bar_stagger);
-        if (t == 0 && wl + 2 < total_layers) load_layer(wl + 2);
+        if (t == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
       }
       mbar_wait(bar_done + 8 * t, wl & 1);
       tc_fence_after();
@@ -240,7 +250,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ply_kernel(SearchParams P, TcArg
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
   }
 }
 

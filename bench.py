@@ -231,7 +231,8 @@ def main():
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
-            traffic = json.load(f).get(dom, {}).get("dram_bytes_per_launch")
+            per = json.load(f).get(dom, {}).get("dram_bytes_per_sim")        # ncu --set full capture of one launch, scaled to the average launch
+            traffic = None if per is None else per * pst["sims"] / classes[dom]["launches"]
     except Exception:
         pass
     nn_tf = f_sim * pst["sims"] / (nn_ms * 1e-3) / 1e12
