@@ -132,7 +132,7 @@ struct EngineT : EngineBase {
   struct GraphSet { int visits, slot, training; std::vector<cudaGraphExec_t> exec; };
   std::vector<GraphSet> graphs;
   // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
-  static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;
+  static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;   // and width 128, checked at run time
   bool use_fused = false;
   int num_sms = 148, fused_min_gpc = 32, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
   // profiling
@@ -204,7 +204,7 @@ struct EngineT : EngineBase {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { err = "no CUDA device (there is no CPU fallback)"; return AGPU_ERR_NO_DEVICE; }
     if (is_tc())
-      AG_REQUIRE(tc_supported(2 * G::VS, cfg.width, cfg.blocks, A), AGPU_ERR_INVALID, "the tensor-core chain does not support this MLP shape yet (width must be 128, 2*VS <= 128, A+1 <= 128)");
+      AG_REQUIRE(tc_supported(2 * G::VS, cfg.width, cfg.blocks, A), AGPU_ERR_INVALID, "the tensor-core chain supports width 128 (2*VS <= 128) and width 512 (2*VS <= 256), heads up to 127 actions");
     AG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, AGPU_ERR_INVALID, "device ordinal out of range");
     AG_CK(cudaSetDevice(cfg.device));
     AG_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -236,7 +236,7 @@ struct EngineT : EngineBase {
     seg_cap = ((L_cap + nseg - 1) / nseg + 255) / 256 * 256;
     if (is_tc()) AG_CK(tc_init());
     if constexpr (FUSED_OK) {
-      if (is_tc()) {
+      if (is_tc() && cfg.width == tc::TC_N) {
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));

@@ -299,15 +299,26 @@ void put_layer(unsigned char* img, int rows_pad, int rows, int kreal, const std:
 
 }  // namespace
 
-int tc_supported(int in, int n, int k, int A) { return n == TC_N && in <= TC_N && k >= 0 && head_n(A) <= TC_N; }
+// width-512 variant (nn_tc512.cu)
+int tc512_supported(int in, int n, int k, int A);
+size_t tc512_image_bytes(int in, int n, int k, int A);
+void tc512_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
+                       const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host, int fmt);
+cudaError_t tc512_init();
+cudaError_t tc512_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt);
+
+int tc_supported(int in, int n, int k, int A) {
+  return (n == TC_N && in <= TC_N && k >= 0 && head_n(A) <= TC_N) || tc512_supported(in, n, k, A);
+}
 
 size_t tc_image_bytes(int in, int n, int k, int A) {
-  (void)in;
+  if (n != TC_N) return tc512_image_bytes(in, n, k, A);
   return (size_t)(1 + k) * n * n * 2 + (size_t)head_n(A) * n * 2;
 }
 
 void tc_build_image(const float* base, const float* const* res, const float* pol_w, const float* pol_b, const float* val_w,
                     const float* val_b, int in, int n, int k, int A, void* img_host, float* bias_host, int fmt) {
+  if (n != TC_N) { tc512_build_image(base, res, pol_w, pol_b, val_w, val_b, in, n, k, A, img_host, bias_host, fmt); return; }
   unsigned char* img = (unsigned char*)img_host;
   std::vector<float> w;
   // base: Julia (n x in) column-major -> row-major [n][in]
@@ -336,10 +347,12 @@ long long* g_tc_dbg = nullptr;   // development: set through agpu_debug_tc_trace
 cudaError_t tc_init() {
   cudaError_t e = cudaFuncSetAttribute(tc_mlp128_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_mlp128_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM);
+  if (e == cudaSuccess) e = tc512_init();
   return e;
 }
 
 cudaError_t tc_forward(const NetDev& net, const NNInput& I, int L, float* out, int outs, cudaStream_t stream, int fmt) {
+  if (net.n != TC_N) return tc512_forward(net, I, L, out, outs, stream, fmt);
   TcArgs T;
   T.img = (const unsigned char*)net.tc_img; T.bias = net.tc_bias; T.nlayers = net.k + 2; T.k0_steps = (net.in + 15) / 16; T.A = net.A;
   T.NH = head_n(net.A); T.in = net.in;

@@ -155,7 +155,7 @@ class Net:
     base (n, in), res[k] (n, n), policy (A, n), policy_bias (A,), value (1, n), value_bias (1,).
     Stored Fortran-ordered so the bytes equal Julia's column-major arrays."""
 
-    FP32, BF16, BF16_RESID, F16 = 0, 1, 2, 3
+    FP32, BF16, BF16_RESID, F16, F16_RESID = 0, 1, 2, 3, 4
 
     def __init__(self, base, res, policy, policy_bias, value, value_bias):
         f = lambda a: np.asfortranarray(np.asarray(a, dtype=np.float32))

@@ -534,12 +534,14 @@ static inline float sigmoidf(float x) { float t = c_expf(-fabsf(x)); return x >=
 // tcgen05 chain computes, up to accumulation order).
 // mode 2: as mode 1 but the residual stream itself is stored in bf16 (wide nets).
 // mode 3: as mode 1 with fp16 operands (saturating) instead of bf16.
+// mode 4: as mode 3 with the residual stream stored in fp16 (wide nets).
 static void net_forward_one(const Net& net, const float* x, float* logits, float* v, int mode, float* b, float* t, float* op) {
   const int n = net.n;
-  const std::vector<float>& Wbase = mode == 3 ? net.base_h : mode ? net.base_r : net.base;
-  const std::vector<float>& Wpol = mode == 3 ? net.policy_h : mode ? net.policy_r : net.policy;
-  const std::vector<float>& Wval = mode == 3 ? net.value_h : mode ? net.value_r : net.value;
-  auto rnd = [mode](float v) { return mode == 3 ? f16_round(v) : mode ? bf16_round(v) : v; };
+  const bool f16m = (mode == 3 || mode == 4);
+  const std::vector<float>& Wbase = f16m ? net.base_h : mode ? net.base_r : net.base;
+  const std::vector<float>& Wpol = f16m ? net.policy_h : mode ? net.policy_r : net.policy;
+  const std::vector<float>& Wval = f16m ? net.value_h : mode ? net.value_r : net.value;
+  auto rnd = [mode, f16m](float v) { return f16m ? f16_round(v) : mode ? bf16_round(v) : v; };
   // b = relu.(base * x)        DenseNet.jl:295
   for (int o = 0; o < n; o++) t[o] = 0.f;
   for (int i = 0; i < net.in; i++) {
@@ -549,9 +551,10 @@ static void net_forward_one(const Net& net, const float* x, float* logits, float
   }
   for (int o = 0; o < n; o++) b[o] = relu(t[o]);
   if (mode == 2) for (int o = 0; o < n; o++) b[o] = bf16_round(b[o]);
+  if (mode == 4) for (int o = 0; o < n; o++) b[o] = f16_round(b[o]);
   // for w in res: b .= relu.(b .+ relu.(w*b))   DenseNet.jl:297-299
   for (int l = 0; l < net.k; l++) {
-    const std::vector<float>& w = mode == 3 ? net.res_h[l] : mode ? net.res_r[l] : net.res[l];
+    const std::vector<float>& w = f16m ? net.res_h[l] : mode ? net.res_r[l] : net.res[l];
     for (int o = 0; o < n; o++) { t[o] = 0.f; op[o] = rnd(b[o]); }
     for (int i = 0; i < n; i++) {
       float bi = op[i];
@@ -559,6 +562,7 @@ static void net_forward_one(const Net& net, const float* x, float* logits, float
     }
     for (int o = 0; o < n; o++) b[o] = relu(b[o] + relu(t[o]));
     if (mode == 2) for (int o = 0; o < n; o++) b[o] = bf16_round(b[o]);
+    if (mode == 4) for (int o = 0; o < n; o++) b[o] = f16_round(b[o]);
   }
   // policy*b .+ policy_bias , σ.(value*b .+ value_bias)     DenseNet.jl:301
   for (int o = 0; o < n; o++) op[o] = rnd(b[o]);
