@@ -260,7 +260,7 @@ struct EngineT : EngineBase {
       const NetSlot& ns = nets[slot];
       tc::TcArgs T;
       T.img = (const unsigned char*)ns.dev.tc_img; T.bias = ns.dev.tc_bias; T.nlayers = ns.dev.k + 2; T.k0_steps = (ns.dev.in + 15) / 16;
-      T.A = ns.dev.A; T.NH = tc::head_n(ns.dev.A); T.in = ns.dev.in; T.dbg = nullptr;
+      T.A = ns.dev.A; T.NH = tc::head_n(ns.dev.A); T.in = ns.dev.in; T.dbg = g_tc_dbg;
       SegParams S; S.off = 0; S.len = (int)L; S.ply = ply; S.training = training; S.seed = seed; S.cpuct = cpuct; S.pad = 0;
       // games per CTA: spread the live games over all CTA slots of the chip (2 per SM with one tile per CTA), at least
       // fused_min_gpc and at most 128 per tile

@@ -113,6 +113,7 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
+  long long t_search = 0, t_nn = 0, t_mark = T.dbg ? clock64() : 0;    // development trace (agpu_debug_tc_trace)
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
     // ================= search phase =================
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       }
     }
     __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
+    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_search += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
     {
@@ -239,7 +241,9 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       }
     }
     __syncthreads();                                                   // nn_out (global) visible to the search phase
+    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_nn += c - t_mark; t_mark = c; }
   }
+  if (T.dbg && threadIdx.x == 0) { T.dbg[blockIdx.x * 4 + 0] = t_search; T.dbg[blockIdx.x * 4 + 1] = t_nn; T.dbg[blockIdx.x * 4 + 2] = count; T.dbg[blockIdx.x * 4 + 3] = visits; }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)
 #pragma unroll 1

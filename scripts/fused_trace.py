@@ -1,0 +1,23 @@
+"""Development: search-phase vs network-phase cycles inside the fused per-ply kernel, per CTA."""
+import ctypes as C, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import alphagpu_b200 as ag
+spec = ag.GameSpec.named("connect4")
+net = ag.ressimplesf(84, 7, 128, 6, seed=0)
+lib = ag._lib.load()
+lib.agpu_debug_tc_trace.argtypes = [C.c_void_p]
+for L in [int(x) for x in sys.argv[1:]] or [32768, 8192, 1024, 128]:
+    ctx = ag.Context(spec, 64, L, 128, 6, 0, 2)
+    ctx.set_weights(net)
+    ctx.re_init(ctx.Position(L))
+    ctx.mcts_single(64, cpuct=1.5, seed=1)
+    buf = torch.zeros(4 * 512, dtype=torch.int64, device="cuda")
+    lib.agpu_debug_tc_trace(C.c_void_p(buf.data_ptr()))
+    ctx.re_init(ctx.Position(L))
+    ctx.mcts_single(64, cpuct=1.5, seed=2)
+    lib.agpu_debug_tc_trace(None)
+    t = buf.cpu().numpy().reshape(-1, 4)
+    t = t[t[:, 3] > 0]
+    print(f"L={L}: CTAs {len(t)} games/CTA {t[:,2].mean():.0f}  per rollout: search {t[:,0].mean()/64:.0f} cyc ({t[:,0].mean()/64/1.965e3:.1f} us)  nn {t[:,1].mean()/64:.0f} cyc ({t[:,1].mean()/64/1.965e3:.1f} us)  max search {t[:,0].max()/64:.0f} max nn {t[:,1].max()/64:.0f}")
+    ctx.close()
