@@ -53,20 +53,35 @@ struct Layout {
   static constexpr int APL = (A + W - 1) / W;                      // actions per lane
   static constexpr int APAD = (W * APL + 7) / 8 * 8;
   static constexpr int GPW = 32 / W;                               // games per warp
-  static constexpr int OFF_PRIOR = 0;
-  static constexpr int OFF_Q = 4 * APAD;
-  static constexpr int OFF_VIS = 8 * APAD;
-  static constexpr int OFF_CHILD = 10 * APAD;
-  static constexpr int OFF_ORDER = 11 * APAD;
   // Small action sets (Connect4, tic-tac-toe): π̄ is stored per node and re-solved in the BACKUP phase, one lane per ancestor,
   // all ancestors of a path in parallel; the descent then only samples.  Equivalent to the reference's solve-at-descent because
   // a node's statistics change only when a backup passes through it (sticky `uptodate`, mcts_gpu.jl:114,321) and the solve is a
   // pure function of them.  Large action sets keep the cooperative solve-at-descent (the network dominates there).
   static constexpr bool FAST = (A <= 9);
-  static constexpr int OFF_POLICY = (12 * APAD + 15) / 16 * 16;
-  static constexpr int OFF_STATE = FAST ? OFF_POLICY + 4 * APAD : (12 * APAD + 7) / 8 * 8;
-  static constexpr int OFF_HDR = OFF_STATE + (int)sizeof(typename G::State);
-  static constexpr int REC = (OFF_HDR + 8 + 31) / 32 * 32;         // record size, multiple of a 32 B sector
+  static constexpr int a16(int x) { return (x + 15) / 16 * 16; }
+  // FAST record: what the descent reads (header, child ids, π̄) sits in the first 64 bytes, so one 64-byte-aligned sector pair
+  // serves a level of the descent; the backup's lane reads the rest.  Other layouts: prior | q | visits | child | order | state | header.
+  static constexpr int OFF_HDR_F = 0;
+  static constexpr int OFF_CHILD_F = 8;
+  static constexpr int OFF_POLICY_F = a16(8 + APAD);
+  static constexpr int OFF_ORDER_F = OFF_POLICY_F + 4 * APAD;
+  static constexpr int OFF_VIS_F = a16(OFF_ORDER_F + APAD);
+  static constexpr int OFF_PRIOR_F = a16(OFF_VIS_F + 2 * APAD);
+  static constexpr int OFF_Q_F = OFF_PRIOR_F + 4 * APAD;
+  static constexpr int OFF_STATE_F = (OFF_Q_F + 4 * APAD + 7) / 8 * 8;
+
+  static constexpr int OFF_PRIOR = FAST ? OFF_PRIOR_F : 0;
+  static constexpr int OFF_Q = FAST ? OFF_Q_F : 4 * APAD;
+  static constexpr int OFF_VIS = FAST ? OFF_VIS_F : 8 * APAD;
+  static constexpr int OFF_CHILD = FAST ? OFF_CHILD_F : 10 * APAD;
+  static constexpr int OFF_ORDER = FAST ? OFF_ORDER_F : 11 * APAD;
+  static constexpr int OFF_POLICY = FAST ? OFF_POLICY_F : 0;           // (FAST only)
+  static constexpr int OFF_STATE = FAST ? OFF_STATE_F : (12 * APAD + 7) / 8 * 8;
+  static constexpr int OFF_HDR = FAST ? OFF_HDR_F : OFF_STATE + (int)sizeof(typename G::State);
+  static constexpr int STATS_BEGIN = FAST ? 8 : 0;                     // [STATS_BEGIN, STATS_END): zeroed when a root is installed
+  static constexpr int STATS_END = OFF_STATE;
+  static constexpr int REC = FAST ? (OFF_STATE + (int)sizeof(typename G::State) + 63) / 64 * 64
+                                  : (OFF_HDR + 8 + 31) / 32 * 32;     // record size
   static constexpr int OUTS = (A + 1 + 3) / 4 * 4;                 // floats per game of network output: logits[A], value
   static_assert(sizeof(typename G::State) % 8 == 0, "state alignment");
 };
@@ -136,10 +151,8 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
   char* rec = P.tree + (size_t)g * P.game_stride;
   if (src) *reinterpret_cast<typename G::State*>(rec + Lay::OFF_STATE) = src[g];
   if (uid) P.uid[g] = uid[g];
-  uint4 z = make_uint4(0, 0, 0, 0);
-  // zero prior|q|visits|child|order (12*APAD bytes, APAD multiple of... at least 1): word stores
-  for (int o = 0; o + 16 <= Lay::OFF_STATE; o += 16) *reinterpret_cast<uint4*>(rec + o) = z;
-  for (int o = Lay::OFF_STATE / 16 * 16; o < Lay::OFF_STATE; o += 4) *reinterpret_cast<uint32_t*>(rec + o) = 0;
+  // zero the statistics (prior, q, visits, child, order, π̄)
+  for (int o = Lay::STATS_BEGIN; o < Lay::STATS_END; o += 8) *reinterpret_cast<uint2*>(rec + o) = make_uint2(0, 0);
   NodeHdr h; h.parent = 0; h.action = 0; h.nchild = 0; h.flags = 0; h.result = 0; h.pad[0] = h.pad[1] = h.pad[2] = 0;
   *reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR) = h;
   P.nnodes[g] = 1;
@@ -153,7 +166,7 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
 // ------------------------------------------------------------------------------------------------
 template <int A, int AP>
 AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis)[AP], const int (&ch)[AP], const int (&ord)[AP],
-                     const int nchild, const float cpuct, float (&pol)[AP]) {
+                     const int nchild, const float cpuct, float (&pol)[AP], const char* q_rec, const char* prior_rec) {
   int nv = 0, acount = 0;
   float rem = 0.f;
 #pragma unroll
@@ -171,28 +184,34 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
     top[a] = fmul(lambda, p[a]);
     alpha = fmaxf(alpha, fadd(q[a], fmaxf(top[a], 1e-4f)));                          // :135-138
   }
-  // statistics of the children in slot order (static selects instead of dynamically indexed registers)
+  // statistics of the children in slot (creation) order, gathered from the record by address — the caller has already stored
+  // the updated q there — instead of 2*A*A register selects
   float tops[AP], qs[AP];
 #pragma unroll
   for (int k = 0; k < A; k++) {
     tops[k] = 0.f; qs[k] = 0.f;
-#pragma unroll
-    for (int a = 0; a < A; a++) if (ord[k] == a + 1) { tops[k] = top[a]; qs[k] = q[a]; }
+    if (k < nchild) {
+      const int a = ord[k] - 1;
+      qs[k] = *reinterpret_cast<const float*>(q_rec + 4 * a);
+      tops[k] = fmul(lambda, *reinterpret_cast<const float*>(prior_rec + 4 * a));
+    }
   }
   float err = __int_as_float(0x7f800000);
   for (int it = 0; it < 100; it++) {                                                 // :141-162
     float S = fdiv(rem, alpha);
-    float gs = fdiv(-rem, fmul(alpha, alpha));
+    float bot[AP];
 #pragma unroll
     for (int k = 0; k < A; k++) {
-      if (k < nchild) {
-        const float bot = fsub(alpha, qs[k]);
-        S = fadd(S, fdiv(tops[k], bot));
-        gs = fadd(gs, fdiv(-tops[k], fmul(bot, bot)));
-      }
+      bot[k] = fsub(alpha, qs[k]);
+      if (k < nchild) S = fadd(S, fdiv(tops[k], bot[k]));
     }
     const float newerr = fsub(S, 1.f);
     if (newerr < 0.001f || newerr == err) break;
+    // the derivative is only needed when the iteration continues (the reference computes it in the same loop and drops it on exit)
+    float gs = fdiv(-rem, fmul(alpha, alpha));
+#pragma unroll
+    for (int k = 0; k < A; k++)
+      if (k < nchild) gs = fadd(gs, fdiv(-tops[k], fmul(bot[k], bot[k])));
     alpha = fsub(alpha, fdiv(newerr, gs));
     err = newerr;
   }
@@ -219,14 +238,18 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
   while (true) {
     char* rec = gbase + (size_t)node * REC;
     const NodeHdr h = *reinterpret_cast<const NodeHdr*>(rec + Lay::OFF_HDR);
-    if (!(h.flags & F_EXPANDED)) break;                                   // while expanded[nindex]==1  (:110)
-
     float p[APL], q[APL], pol[APL];
     int vis[APL], ch[APL], ord[APL];
     if constexpr (Lay::FAST) {
+      // header, child ids and π̄ share the record's first 64 bytes: all three loads are issued before the flag is tested
       static_assert(APL == 1, "FAST layouts have one action per lane");
       pol[0] = l < A ? *reinterpret_cast<const float*>(rec + Lay::OFF_POLICY + 4 * l) : 0.f;   // π̄ as left by expand / the last backup
       ch[0] = l < A ? (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_CHILD + l) : 0;
+    }
+    if (!(h.flags & F_EXPANDED)) break;                                   // while expanded[nindex]==1  (:110)
+    if constexpr (Lay::FAST) {
+      // the next node is one of the children: pull their first sectors towards L1 while this level is sampled
+      if (ch[0] != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(gbase + (size_t)(ch[0] - 1) * REC));
     } else {
 #pragma unroll
     for (int j = 0; j < APL; j++) {
@@ -511,7 +534,7 @@ AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, co
         *reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * mv) = qnew;
         *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * mv) = (uint16_t)(vold + 1);
         if (!last_rollout) {
-          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol);
+          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol, nrec + Lay::OFF_Q, nrec + Lay::OFF_PRIOR);
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
             *reinterpret_cast<float4*>(nrec + Lay::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
