@@ -26,7 +26,7 @@ template <int NT> struct FCfg {
   static constexpr int THREADS = 512 * NT;
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 1024;
+  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 10240;   // + alignment slack + barriers/bias/backup work list
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
   static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
 };
@@ -63,6 +63,10 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   // bars[0..2] full, [3..5] empty, [6..7] mma_done, [8] stagger (one-shot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
   float* sbias = reinterpret_cast<float*>(bars + 10);                  // [128] head biases
+  // work list of the backup phase: per game of the CTA the leaf evaluation, the path length and its exclusive prefix sum
+  LeafEval* s_eval = reinterpret_cast<LeafEval*>(bars + 80);           // [256]
+  int* s_d = reinterpret_cast<int*>(s_eval + C::GAMES);                // [256]
+  int* s_off = s_d + C::GAMES;                                         // [257]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
@@ -117,16 +121,50 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
     // ================= search phase =================
+    if (k > 0) {
+      // (a) expand every game of the CTA (softmax, legal mask, prior), leaving value and path length in shared memory
+#pragma unroll 1
+      for (int p = 0; p < PASSES; p++) {
+        const int gl = p * GROUPS + sg;
+        const int g = S.off + cta_first + gl;
+        if (g < L_end) {
+          const LeafEval E = expand_game<G, false>(P, g, sl, gm, S.training, 0, nullptr, nullptr);
+          if (sl == 0) { s_eval[gl] = E; s_d[gl] = P.path_len[g]; }
+        } else if (sl == 0) {
+          s_d[gl] = 0;
+        }
+      }
+      __syncthreads();
+      // (b) exclusive prefix sum of the path lengths (warp 0, GAMES/32 entries per lane)
+      if (warp == 0) {
+        constexpr int PER = C::GAMES / 32;
+        int loc[PER], sum = 0;
+#pragma unroll
+        for (int i = 0; i < PER; i++) { loc[i] = sum; sum += s_d[lane * PER + i]; }
+        int incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+        const int excl = incl - sum;
+#pragma unroll
+        for (int i = 0; i < PER; i++) s_off[lane * PER + i] = excl + loc[i];
+        if (lane == 31) s_off[C::GAMES] = incl;
+      }
+      __syncthreads();
+      // (c) backUp + re-solve of π̄: one (game, ancestor) item per THREAD, packed densely over the CTA — with a lane group per
+      //     game only d of its 8 lanes (46 % on average) had an ancestor to work on, and the solve is 40 % of the search time
+      const int items = s_off[C::GAMES];
+      for (int i = threadIdx.x; i < items; i += C::THREADS) {
+        int lo = 0, hi = C::GAMES;                                     // largest gl with s_off[gl] <= i
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+        backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct);
+      }
+      __syncthreads();
+    }
+    // (d) descent of this rollout
 #pragma unroll 1
     for (int p = 0; p < PASSES; p++) {
       const int g = S.off + cta_first + p * GROUPS + sg;
-      if (g < L_end) {
-        if (k > 0) {
-          expand_backup_game<G, false>(P, g, sl, gm, S.training, 0, nullptr, nullptr, S.cpuct);
-          __syncwarp(gm);
-        }
-        select_game<G>(P, g, sl, gm, 0, k, last, S.cpuct, nullptr, S.seed, S.ply);
-      }
+      if (g < L_end) select_game<G>(P, g, sl, gm, 0, k, last, S.cpuct, nullptr, S.seed, S.ply);
     }
     __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_search += c - t_mark; t_mark = c; }

@@ -409,9 +409,17 @@ __global__ void __launch_bounds__(256, AG_MINBLOCKS) select_kernel(SearchParams 
 // expand + backUp (mcts_gpu.jl:250-328), with softmax! (:417) when the prior comes from the network.
 // INJECT: prior_in[L][A] is already softmaxed (what `expand` receives), value_in[L].
 // ------------------------------------------------------------------------------------------------
+// what expand leaves for the backup of the same game
+struct LeafEval {
+  float v;            // network value of the leaf (non-terminal)
+  double value0_d;    // terminal value (1 + player*r)/2, a Float64 in the reference (:314)
+  int term;           // leaf is terminal
+  int parent, action; // vnodes.parent / actionFromParent of the leaf (1-based, 0 = none)
+};
+
 template <class G, bool INJECT>
-AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, const unsigned gm, int training, int last_rollout,
-                             const float* __restrict__ prior_in, const float* __restrict__ value_in, const float cpuct) {
+AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const unsigned gm, int training, int last_rollout,
+                          const float* __restrict__ prior_in, const float* __restrict__ value_in) {
   typedef Layout<G> Lay;
   constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
   char* gbase = P.tree + (size_t)g * P.game_stride;
@@ -473,18 +481,28 @@ AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, co
     if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
   }
 
-  // backUp: :306-328
-  if constexpr (Lay::FAST) {
-    // Lane-parallel backup: lane jj takes the jj-th node of the recorded path (0 = root).  Each ancestor is a different node, so
-    // the running-mean updates are independent; the value each one receives is the leaf value flipped once per level below it
-    // (value = 1 - value, :324), evaluated as that literal chain.  The lane then re-solves π̄ of its node (solve_node) — except
-    // after the last rollout, whose π̄ nobody reads (policy_final is the root policy of the last DESCENT, :443).
-    constexpr int AP = Lay::APAD;
-    const int d = P.path_len[g];
-    const double value0_d = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;   // terminal: Float64 in the reference (:314)
-    for (int base = 0; base < d; base += W) {
-      const int jj = base + l;
-      if (jj < d) {
+  LeafEval E;
+  E.v = v; E.term = term ? 1 : 0; E.parent = h.parent; E.action = h.action;
+  E.value0_d = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;
+  (void)gbase; (void)REC;
+  return E;
+}
+
+// One ancestor of one game, by one lane (FAST layouts): running mean of the child's value (:319-320) and the re-solve of π̄.
+// jj = index in the recorded path (0 = root), d = path length.  Each ancestor is a different node, so items are independent;
+// the value an ancestor receives is the leaf value flipped once per level below it (value = 1 - value, :324), evaluated as that
+// literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
+template <class G>
+AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct) {
+  typedef Layout<G> Lay;
+  constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
+  char* gbase = P.tree + (size_t)g * P.game_stride;
+  const bool term = E.term != 0;
+  const float v = E.v;
+  const double value0_d = E.value0_d;
+  {
+    {
+      {
         const int flips = d - 1 - jj;
         const int nd = P.path_node[(size_t)g * P.R + jj];
         const int mv = P.path_move[(size_t)g * P.R + jj];
@@ -541,13 +559,33 @@ AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, co
         }
       }
     }
+  }
+}
+
+template <class G, bool INJECT>
+AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, const unsigned gm, int training, int last_rollout,
+                             const float* __restrict__ prior_in, const float* __restrict__ value_in, const float cpuct) {
+  typedef Layout<G> Lay;
+  constexpr int W = Lay::W, REC = Lay::REC;
+  char* gbase = P.tree + (size_t)g * P.game_stride;
+  const LeafEval E = expand_game<G, INJECT>(P, g, l, gm, training, last_rollout, prior_in, value_in);
+  // backUp: :306-328
+  if constexpr (Lay::FAST) {
+    // lane-parallel: lane jj takes the jj-th node of the recorded path
+    const int d = P.path_len[g];
+    for (int base = 0; base < d; base += W) {
+      const int jj = base + l;
+      if (jj < d) backup_item<G>(P, g, jj, d, E, last_rollout, cpuct);
+    }
     return;
   }
-  int nindex = h.parent;
-  int move = h.action;
+  const bool term = E.term != 0;
+  const float v = E.v;
+  int nindex = E.parent;
+  int move = E.action;
   if (term) {
     // value = (1 + player*r)/2 is a Float64 in the reference (:314): the running mean on this path is evaluated in double
-    double value = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;
+    double value = E.value0_d;
     while (nindex != 0) {
       char* nrec = gbase + (size_t)(nindex - 1) * REC;
       if (l == ((move - 1) % W)) {
