@@ -126,12 +126,12 @@ def test_tc_selfplay_properties_full_size():
     ctx.close()
 
 
-def test_fused_ply_kernel_equals_separate_kernels(monkeypatch):
+@pytest.mark.parametrize("name,games,R", [("connect4", 3000, 24), ("ttt", 1500, 16), ("connect4", 40000, 8)])
+def test_fused_ply_kernel_equals_separate_kernels(monkeypatch, name, games, R):
     """The persistent per-ply kernel (fused.cuh) and the per-rollout kernels (search.cuh + nn_tc.cu) run the same device functions
-    and the same MMA sequence: a whole self-play generation must come out identical, bit for bit."""
-    name = "connect4"
+    and the same MMA sequence: a whole self-play generation must come out identical, bit for bit.  Game counts that are not
+    multiples of 256 exercise partially filled tiles and CTAs; 40000 games exceed one CTA per SM (full 256-game CTAs)."""
     pnet, _ = make_nets(GAME_SPECS[name], 128, 6, seed=11)
-    games, R = 3000, 24          # not a multiple of 256: exercises partially filled tiles and CTAs
     outs = []
     for fused in ("1", "0"):
         monkeypatch.setenv("AGPU_FUSED", fused)
