@@ -4,6 +4,8 @@ The compute lives in libalphagpu.so (CUDA, sm_100a; C ABI in include/alphagpu.h)
 Python host-side mirror of the reference's `mcts_gpu` module and game-plugin interface.
 """
 from . import _lib  # noqa: F401
-from .densenet import SNetwork2, ressimplesf  # noqa: F401
+from .densenet import NetworkF, SNetwork2, convert_back, load_network, ressimplesf, ressimplesf_full, save_network  # noqa: F401
 from .game import GameSpec  # noqa: F401
 from .mcts_gpu import Context, PoolSample, duelnetwork, init, mcts, mcts_duel  # noqa: F401
+from .train import Trainer, traininPipe  # noqa: F401
+from .selfplay import elo_update, trainingPipeline  # noqa: F401

@@ -46,6 +46,13 @@ class KernelTimes(C.Structure):
     _fields_ = [("launches", C.c_int64 * NKERNELS), ("ms", C.c_double * NKERNELS), ("nodes_traversed", C.c_int64), ("descents", C.c_int64)]
 
 
+class TrainConfig(C.Structure):
+    _fields_ = [("device", C.c_int32), ("inp", C.c_int32), ("width", C.c_int32), ("blocks", C.c_int32), ("actions", C.c_int32),
+                ("fsize", C.c_int32), ("max_batch", C.c_int32), ("reserved", C.c_int32), ("lr", C.c_double), ("beta1", C.c_double),
+                ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double), ("feature_weight", C.c_float),
+                ("reserved2", C.c_float)]
+
+
 # every symbol include/alphagpu.h declares, with its signature
 _VP, _I32, _I64, _U32, _U64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
 SIGNATURES = {
@@ -85,6 +92,25 @@ class AlphaGPUError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libalphagpu error {code}: {msg}")
         self.code = code
+
+
+# include/alphagpu_train.h
+_W8 = [C.c_void_p] * 8
+SIGNATURES.update({
+    "agpu_trainer_create": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(TrainConfig)]),
+    "agpu_trainer_destroy": (None, [C.c_void_p]),
+    "agpu_trainer_last_error": (C.c_char_p, [C.c_void_p]),
+    "agpu_trainer_set_params": (C.c_int, [C.c_void_p, *_W8, C.c_int32]),
+    "agpu_trainer_get_params": (C.c_int, [C.c_void_p, *_W8]),
+    "agpu_trainer_get_grads": (C.c_int, [C.c_void_p, *_W8]),
+    "agpu_trainer_loss_grad": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
+    "agpu_trainer_loss": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
+    "agpu_trainer_step": (C.c_int, [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]),
+    "agpu_trainer_grad_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "agpu_trainer_apply": (C.c_int, [C.c_void_p, C.c_float]),
+    "agpu_trainer_opt_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]),
+    "agpu_trainer_last_ms": (C.c_int, [C.c_void_p, C.c_void_p]),
+})
 
 
 def load():

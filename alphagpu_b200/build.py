@@ -15,14 +15,15 @@ OBJ = os.path.join(HERE, "_obj")
 SO = os.path.join(HERE, "libalphagpu.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
-SOURCES = ["api.cu", "engine_connect4.cu", "engine_gobang.cu", "engine_hex.cu", "engine_reversi.cu", "nn_tc.cu", "nn_tc512.cu"]
+SOURCES = ["api.cu", "engine_connect4.cu", "engine_gobang.cu", "engine_hex.cu", "engine_reversi.cu", "nn_tc.cu", "nn_tc512.cu", "train.cu"]
 # --fmad=false: the search / fp32-NN arithmetic is specified operation by operation (canonical fp32)
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--expt-relaxed-constexpr",
          "--fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-fast-math", "-Xcompiler", "-ffp-contract=off"]
 
 
 def _deps():
-    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "alphagpu.h")]
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "alphagpu.h"),
+                                                                os.path.join(HERE, "..", "include", "alphagpu_train.h")]
 
 
 def _stale(target, deps):

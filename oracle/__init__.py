@@ -16,6 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SRC = os.path.join(_HERE, "oracle.cpp")
+_SRCS = [_SRC, os.path.join(_HERE, "train_oracle.cpp")]
 
 CONNECT4, GOBANG, HEX, REVERSI8, REVERSI6 = 0, 1, 2, 3, 4
 
@@ -48,9 +49,9 @@ def build_all(force: bool = False) -> None:
 
 def build(force: bool = False) -> str:
     """Compile oracle.cpp -> oracle/_build/liboracle[_avx2].so (g++, seconds)."""
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(f) for f in _SRCS):
         os.makedirs(os.path.dirname(_SO), exist_ok=True)
-        subprocess.check_call(["g++", *CXXFLAGS, *(["-mavx2"] if _AVX2 else []), "-o", _SO, _SRC])
+        subprocess.check_call(["g++", *CXXFLAGS, *(["-mavx2"] if _AVX2 else []), "-o", _SO, *_SRCS])
     return _SO
 
 
@@ -87,6 +88,15 @@ def lib():
         _lib.orc_net_create.restype = C.c_void_p
         _lib.orc_tree_create.restype = C.c_void_p
         _lib.orc_tree_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64]
+        _lib.orc_trainer_create.restype = C.c_void_p
+        _lib.orc_trainer_create.argtypes = [C.c_int] * 5 + [C.c_double] * 5 + [C.c_float]
+        _lib.orc_trainer_count.restype = C.c_int64
+        for f in ("orc_trainer_destroy", "orc_trainer_count", "orc_trainer_reset_opt"):
+            getattr(_lib, f).argtypes = [C.c_void_p]
+        _lib.orc_trainer_get.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_trainer_set.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        _lib.orc_trainer_loss_grad.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p, C.c_int]
+        _lib.orc_trainer_apply.argtypes = [C.c_void_p, C.c_float]
     return _lib
 
 
@@ -377,3 +387,77 @@ def num_threads() -> int:
 
 def set_num_threads(n: int):
     lib().orc_set_num_threads(int(n))
+
+
+class Trainer:
+    """One `networkf` + Optimiser(ADAM(lr), WeightDecay(wd)) (train.jl:12-15,47-51,128-162; oracle/train_oracle.cpp).
+
+    Parameters travel as a dict of Julia column-major arrays: base (n,in), res [k x (n,n)], pol_w (A,n), pol_b (A), val_w (1,n),
+    val_b (1), feat_w (FS,n), feat_b (FS) — numpy arrays in Fortran order or any array whose .T is the row-major transpose.
+    """
+    PARAMS, GRADS, M, V = 0, 1, 2, 3
+
+    def __init__(self, inp: int, n: int, k: int, A: int, FS: int, lr=0.001, beta1=0.9, beta2=0.999, eps=1e-8, wd=1e-4, fweight=0.001):
+        self.inp, self.n, self.k, self.A, self.FS, self.NH = inp, n, k, A, FS, A + 1 + FS
+        self._h = C.c_void_p(lib().orc_trainer_create(inp, n, k, A, FS, lr, beta1, beta2, eps, wd, fweight))
+        self.P = int(lib().orc_trainer_count(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_trainer_destroy(self._h)
+            self._h = None
+
+    # flat layout: base | res | heads packed (NH x n) column-major | head biases
+    def pack(self, d) -> np.ndarray:
+        cm = lambda a, r, c: np.asarray(a, np.float32).reshape(r, c, order="F") if np.asarray(a).ndim == 1 else np.asarray(a, np.float32)
+        heads = np.concatenate([cm(d["pol_w"], self.A, self.n), cm(d["val_w"], 1, self.n), cm(d["feat_w"], self.FS, self.n)], axis=0)
+        parts = [cm(d["base"], self.n, self.inp).ravel(order="F")] + [cm(w, self.n, self.n).ravel(order="F") for w in d["res"]]
+        parts += [heads.ravel(order="F"), np.asarray(d["pol_b"], np.float32).ravel(), np.asarray(d["val_b"], np.float32).ravel(),
+                  np.asarray(d["feat_b"], np.float32).ravel()]
+        flat = np.ascontiguousarray(np.concatenate(parts), dtype=np.float32)
+        assert flat.size == self.P
+        return flat
+
+    def unpack(self, flat: np.ndarray):
+        n, k, A, FS, NH, inp = self.n, self.k, self.A, self.FS, self.NH, self.inp
+        o = 0
+        base = flat[o:o + n * inp].reshape(n, inp, order="F"); o += n * inp
+        res = []
+        for _ in range(k):
+            res.append(flat[o:o + n * n].reshape(n, n, order="F")); o += n * n
+        heads = flat[o:o + NH * n].reshape(NH, n, order="F"); o += NH * n
+        bias = flat[o:o + NH]
+        return dict(base=base, res=res, pol_w=heads[:A], val_w=heads[A:A + 1], feat_w=heads[A + 1:], pol_b=bias[:A], val_b=bias[A:A + 1],
+                    feat_b=bias[A + 1:])
+
+    def set(self, which: int, flat: np.ndarray):
+        flat = np.ascontiguousarray(flat, dtype=np.float32)
+        assert flat.size == self.P
+        assert lib().orc_trainer_set(self._h, which, _p(flat)) == 0
+
+    def get(self, which: int) -> np.ndarray:
+        out = np.zeros(self.P, np.float32)
+        assert lib().orc_trainer_get(self._h, which, _p(out)) == 0
+        return out
+
+    def set_params(self, d, reset_optimizer=True):
+        self.set(self.PARAMS, self.pack(d))
+        if reset_optimizer:
+            lib().orc_trainer_reset_opt(self._h)
+
+    def loss_grad(self, state, policy, value, fstate, want_grad=True) -> np.ndarray:
+        state = np.ascontiguousarray(state, np.int8); policy = np.ascontiguousarray(policy, np.float32)
+        value = np.ascontiguousarray(value, np.float32).ravel(); fstate = np.ascontiguousarray(fstate, np.int8)
+        B = state.shape[0]
+        assert state.shape == (B, self.inp) and policy.shape == (B, self.A) and value.shape == (B,) and fstate.shape == (B, self.FS)
+        out = np.zeros(4, np.float32)
+        assert lib().orc_trainer_loss_grad(self._h, _p(state), _p(policy), _p(value), _p(fstate), B, _p(out), int(want_grad)) == 0
+        return out
+
+    def apply(self, gscale: float = 1.0):
+        assert lib().orc_trainer_apply(self._h, gscale) == 0
+
+    def step(self, state, policy, value, fstate) -> np.ndarray:
+        out = self.loss_grad(state, policy, value, fstate)
+        self.apply(1.0)
+        return out
