@@ -262,6 +262,36 @@ def main():
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
     }
 
+    # ---- the training step that follows a generation (train.jl): batch 8192 (main4IARow.jl:102-105) split over the ranks,
+    #      gradient all-reduce over NCCL when world > 1.  An extra, not part of the headline metric; never allowed to break the line. ----
+    try:
+        tnet = ag.ressimplesf_full(2 * spec.VectorizedState, spec.maxActions, spec.FeatureSize, WIDTH, BLOCKS, seed=0)
+        TB = 8192
+        trainer = ag.Trainer.for_network(tnet, TB // world, device=local_rank)
+        rng = np.random.default_rng(1)
+        st = (rng.random((TB, 2 * spec.VectorizedState)) < 0.3).astype(np.int8)
+        pol = rng.random((TB, spec.maxActions)).astype(np.float32); pol /= pol.sum(1, keepdims=True)
+        val = rng.choice(np.array([0, 0.5, 1], np.float32), size=TB)
+        fst = rng.integers(-1, 2, size=(TB, spec.FeatureSize)).astype(np.int8)
+        sl = ag.train.dp_slice(TB, rank, world)
+        tb = [a[sl] for a in (st, pol, val, fst)]
+        tstep = (lambda: trainer.step_dp(*tb)) if world > 1 else (lambda: trainer.step(*tb))
+        for _ in range(3):
+            tstep()
+        sync()
+        t0 = time.perf_counter()
+        tdev = []
+        for _ in range(20):
+            tstep()
+            tdev.append(sum(trainer.last_ms()))
+        sync()
+        twall = (time.perf_counter() - t0) / 20
+        line["train_step"] = {"net": "networkf 128x6 + feature head, fp32", "global_batch": TB, "ms_per_step_e2e": 1e3 * twall, "ms_per_step_device": float(np.median(tdev)),
+                              "samples_per_s": TB / twall, "allreduce": "nccl sum of one flat fp32 gradient" if world > 1 else None}
+        trainer.close()
+    except Exception as e:                                                       # pragma: no cover
+        line["train_step"] = {"error": repr(e)}
+
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (N=1 only) ----
     if world == 1 and not args.no_cpu_baseline:
         import oracle
