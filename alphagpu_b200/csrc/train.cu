@@ -7,7 +7,7 @@
 // policy, value, feature — and the NH head biases; every matrix Julia column-major, i.e. element (out o, in i) at o + outs*i,
 // which is exactly the row-major [K = in][N = out] operand the forward product wants.
 //
-// Arithmetic contract (bit-exact against oracle/train_oracle.cpp): every product is an fma chain ascending in k starting from
+// Arithmetic contract (the CPU checker of the tests restates it bit for bit): every product is an fma chain ascending in k starting from
 // +0; weight gradients are accumulated per slice of TRAIN_KSLICE = 256 samples and the slices added in ascending order;
 // element-wise steps are single IEEE operations in the order written here; exp/sigmoid/tanh are the canonical c_expf forms;
 // Adam + weight decay run per element in fp64 and round once per stored value, as Flux 0.12.6's broadcasts over Float64
