@@ -225,17 +225,55 @@ def init(spec: GameSpec, visits: int, ngames: int, actor: SNetwork2, device: int
     return ctx
 
 
+def _world():
+    """(rank, world, backend) of the default torch.distributed group, (0, 1, None) outside one."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist.get_rank(), dist.get_world_size(), dist.get_backend()
+    except ImportError:
+        pass
+    return 0, 1, None
+
+
+def _sum_over_ranks(values, device):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(v) for v in values], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return [int(v) for v in t.tolist()]
+
+
 def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample], *, spec: GameSpec, cpuct=2.0, noise=None, seed=0,
          uid_base=0, device=0, nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
     """mcts(actor, visits, ngames, buffer; cpuct, noise) (mcts_gpu.jl:477-579): one generation of self-play; samples are
-    pushed into `buffer`.  Returns (data, valid) like the reference plus the run statistics."""
+    pushed into `buffer`.  Returns (data, valid) like the reference plus the run statistics.
+
+    Under torch.distributed (one process per GPU) the `ngames` games are block-partitioned over the ranks by uid — no collective on
+    the search path — and the sample blocks are all-gathered afterwards, so every rank pushes the same samples in the same order
+    (rank-major) into its buffer; results and counters are summed over ranks."""
+    rank, world, backend = _world()
+    if world > 1:
+        from .parallel import gather_samples, shard_games
+        base, count = shard_games(ngames, rank, world)
+        uid_base, ngames_local = uid_base + base, count
+    else:
+        ngames_local = ngames
     own = ctx is None
     if own:
-        ctx = init(spec, visits, ngames, actor, device, nn_mode)
+        ctx = init(spec, visits, max(1, ngames_local), actor, device, nn_mode)
     else:
         ctx.set_weights(actor, 0)
     noise = float(2.0 / spec.maxActions) if noise is None else noise
-    res, stats, out = ctx.selfplay(visits, ngames, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
+    res, stats, out = ctx.selfplay(visits, ngames_local, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
+    if world > 1:
+        dev = f"cuda:{device}" if backend == "nccl" else None
+        if buffer is not None:
+            out = gather_samples({k: out[k] for k in ("state", "policy", "player", "value", "fstate")}, device=dev)
+        keys = ("sims", "positions", "plies", "total_length", "faults", "kernel_launches")
+        tot = _sum_over_ranks(list(res) + [stats[k] for k in keys], dev)
+        res = np.asarray(tot[:3], np.int64)
+        stats.update(dict(zip(keys, tot[3:])))
     if buffer is not None:
         buffer.push_block(out["state"], out["policy"], out["player"], out["value"], out["fstate"])
     if own:
@@ -246,15 +284,23 @@ def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample
 
 def mcts_duel(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, cpuct=2.0, seed=0, device=0,
               nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
-    """mcts(actor1, actor2, visits, ngames; cpuct) (mcts_gpu.jl:581-651) -> [v, n, d]."""
+    """mcts(actor1, actor2, visits, ngames; cpuct) (mcts_gpu.jl:581-651) -> [v, n, d].  Under torch.distributed the games are
+    block-partitioned over the ranks and the three counts summed."""
+    rank, world, backend = _world()
+    uid_base = 0
+    if world > 1:
+        from .parallel import shard_games
+        uid_base, ngames = shard_games(ngames, rank, world)
     own = ctx is None
     if own:
-        ctx = Context(spec, visits, ngames, actor1.width, actor1.blocks, device, nn_mode)
+        ctx = Context(spec, visits, max(1, ngames), actor1.width, actor1.blocks, device, nn_mode)
     ctx.set_weights(actor1, 0)
     ctx.set_weights(actor2, 1)
-    res, _ = ctx.duel(visits, ngames, cpuct=cpuct, seed=seed)
+    res, _ = ctx.duel(visits, ngames, cpuct=cpuct, seed=seed, uid_base=uid_base)
     if own:
         ctx.close()
+    if world > 1:
+        res = np.asarray(_sum_over_ranks(res, f"cuda:{device}" if backend == "nccl" else None), np.int64)
     return res
 
 
