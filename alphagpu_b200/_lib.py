@@ -83,6 +83,7 @@ SIGNATURES = {
     "agpu_get_kernel_times": (C.c_int, [_VP, C.POINTER(KernelTimes), _I32]),
     "agpu_layout_info": (C.c_int, [_VP, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
     "agpu_debug_expf": (C.c_int, [_VP, _VP, _I64, _VP, _I32]),
+    "agpu_debug_fdiv_check": (C.c_int, [_U64, _U64, _VP]),
 }
 
 _lib = None

@@ -16,6 +16,30 @@ __global__ void debug_expf_kernel(const float* x, long long n, float* y, int sig
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = sigmoid ? c_sigmoidf(x[i]) : c_expf(x[i]);
 }
+// fdiv_fast against __fdiv_rn on random operands of its box (and a band outside it, where `bad` must be raised whenever they differ)
+__global__ void debug_fdiv_kernel(unsigned long long n_per_thread, unsigned long long seed, unsigned long long* out) {
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long mism = 0, flagged = 0;
+  for (unsigned long long i = 0; i < n_per_thread; i += 2) {
+    const Philox4 r = philox4x32_10((u32)tid, (u32)(tid >> 32), (u32)i, (u32)(i >> 32), (u32)seed, (u32)(seed >> 32));
+    for (int h = 0; h < 2; h++) {
+      const u32 wa = r.v[2 * h], wb = r.v[2 * h + 1];
+      // exponent field 60..194: the box is 67..187, so ~10 % of the operands fall outside it
+      const u32 ea = 60u + (wa >> 9) % 135u, eb = 60u + (wb >> 9) % 135u;
+      // mostly positive operands (the box), a negative sign one time in sixteen
+      float a = __uint_as_float((wa & 0x007FFFFFu) | (ea << 23) | ((wa >> 28) == 0 ? 0x80000000u : 0u));
+      const float b = __uint_as_float((wb & 0x007FFFFFu) | (eb << 23) | ((wb >> 28) == 0 ? 0x80000000u : 0u));
+      if ((wa & 0x7F000u) == 0) a = (wa & 0x08000000u) ? -0.f : 0.f;         // zeros of both signs now and then
+      const bool bad = !(fdiv_box_num(a) && fdiv_box_den(b));
+      const float f = fdiv_fast(a, b);
+      const float t = __fdiv_rn(a, b);
+      if (bad) flagged++;
+      else if (__float_as_uint(f) != __float_as_uint(t)) mism++;
+    }
+  }
+  atomicAdd(&out[0], mism);
+  atomicAdd(&out[1], flagged);
+}
 }  // namespace ag
 
 static bool fill_info(int32_t game, int32_t n, int32_t nvict, agpu_game_info* o) {
@@ -175,6 +199,21 @@ int agpu_layout_info(agpu_ctx* ctx, int64_t* node_bytes, int64_t* game_bytes, in
 /* development hook: device buffer receiving clock64 stamps of the tensor-core chain ([cta][tile][16 layers][4]); NULL disables */
 int agpu_debug_tc_trace(void* dev_buf) { ag::g_tc_dbg = (long long*)dev_buf; return AGPU_OK; }
 /* test hook: the canonical exp / sigmoid evaluated on the device */
+int agpu_debug_fdiv_check(uint64_t pairs, uint64_t seed, uint64_t out[2]) {
+  if (!out) return AGPU_ERR_INVALID;
+  unsigned long long* d = nullptr;
+  if (cudaMalloc((void**)&d, 16) != cudaSuccess) return AGPU_ERR_CUDA;
+  cudaMemset(d, 0, 16);
+  const int blocks = 148 * 8, threads = 256;
+  const unsigned long long per = (pairs + (unsigned long long)blocks * threads - 1) / ((unsigned long long)blocks * threads);
+  ag::debug_fdiv_kernel<<<blocks, threads>>>((per + 1) & ~1ull, seed, d);
+  unsigned long long h[2] = {0, 0};
+  const cudaError_t e = cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return AGPU_ERR_CUDA;
+  out[0] = h[0]; out[1] = h[1];
+  return AGPU_OK;
+}
 int agpu_debug_expf(agpu_ctx* ctx, const float* x, int64_t n, float* y, int32_t sigmoid) {
   CTX_OR_FAIL();
   if (!x || !y || n < 1) return AGPU_ERR_INVALID;

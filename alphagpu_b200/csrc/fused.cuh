@@ -117,24 +117,24 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
-  long long t_search = 0, t_nn = 0, t_mark = T.dbg ? clock64() : 0;    // development trace (agpu_debug_tc_trace)
+  long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): expand, scan, backup, select, network
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
     // ================= search phase =================
     if (k > 0) {
       // (a) expand every game of the CTA (softmax, legal mask, prior), leaving value and path length in shared memory
-#pragma unroll 1
-      for (int p = 0; p < PASSES; p++) {
-        const int gl = p * GROUPS + sg;
+      if (threadIdx.x < C::GAMES) {                                    // one thread per game (search.cuh: expand_game1)
+        const int gl = threadIdx.x;
         const int g = S.off + cta_first + gl;
         if (g < L_end) {
-          const LeafEval E = expand_game<G, false>(P, g, sl, gm, S.training, 0, nullptr, nullptr);
-          if (sl == 0) { s_eval[gl] = E; s_d[gl] = P.path_len[g]; }
-        } else if (sl == 0) {
+          s_eval[gl] = expand_game1<G>(P, g, S.training, 0);
+          s_d[gl] = P.path_len[g];
+        } else {
           s_d[gl] = 0;
         }
       }
       __syncthreads();
+      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[0] += c - t_mark; t_mark = c; }
       // (b) exclusive prefix sum of the path lengths (warp 0, GAMES/32 entries per lane)
       if (warp == 0) {
         constexpr int PER = C::GAMES / 32;
@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
         if (lane == 31) s_off[C::GAMES] = incl;
       }
       __syncthreads();
+      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[1] += c - t_mark; t_mark = c; }
       // (c) backUp + re-solve of π̄: one (game, ancestor) item per THREAD, packed densely over the CTA — with a lane group per
       //     game only d of its 8 lanes (46 % on average) had an ancestor to work on, and the solve is 40 % of the search time
       const int items = s_off[C::GAMES];
@@ -159,15 +160,12 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
         backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct);
       }
       __syncthreads();
+      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // (d) descent of this rollout
-#pragma unroll 1
-    for (int p = 0; p < PASSES; p++) {
-      const int g = S.off + cta_first + p * GROUPS + sg;
-      if (g < L_end) select_game<G>(P, g, sl, gm, 0, k, last, S.cpuct, nullptr, S.seed, S.ply);
-    }
+    if (threadIdx.x < count) select_game1<G>(P, S.off + cta_first + (int)threadIdx.x, k, last, S.seed, S.ply);
     __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
-    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_search += c - t_mark; t_mark = c; }
+    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
     {
@@ -279,9 +277,12 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       }
     }
     __syncthreads();                                                   // nn_out (global) visible to the search phase
-    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_nn += c - t_mark; t_mark = c; }
+    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
-  if (T.dbg && threadIdx.x == 0) { T.dbg[blockIdx.x * 4 + 0] = t_search; T.dbg[blockIdx.x * 4 + 1] = t_nn; T.dbg[blockIdx.x * 4 + 2] = count; T.dbg[blockIdx.x * 4 + 3] = visits; }
+  if (T.dbg && threadIdx.x == 0) {
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 8 + i] = t_ph[i];
+    T.dbg[blockIdx.x * 8 + 5] = count; T.dbg[blockIdx.x * 8 + 6] = visits;
+  }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)
 #pragma unroll 1

@@ -196,27 +196,64 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
       tops[k] = fmul(lambda, *reinterpret_cast<const float*>(prior_rec + 4 * a));
     }
   }
+  // Fast-division plan (common.cuh: fdiv_fast): every numerator below is loop-invariant and non-negative, every denominator positive.
+  // The derivative is summed with all signs flipped, G = rem/α² + Σ tops/bot² = -gs: rounding is sign-symmetric, so -G is bit for bit the
+  // reference's gs, and α - err/gs = α + err/G.  Denominators are box-checked through their running min / max.
+  constexpr float SQ_LO = 9.313225746154785e-10f, SQ_HI = 1073741824.0f;             // 2^-30, 2^30: the squares stay inside the box
+  bool num_ok = fdiv_box_num(rem);
+#pragma unroll
+  for (int k = 0; k < A; k++) num_ok = num_ok && fdiv_box_num(tops[k]);
   float err = __int_as_float(0x7f800000);
   for (int it = 0; it < 100; it++) {                                                 // :141-162
-    float S = fdiv(rem, alpha);
-    float bot[AP];
+    float bot[AP], t1[AP];
+    float bmin = alpha, bmax = alpha;
 #pragma unroll
-    for (int k = 0; k < A; k++) {
-      bot[k] = fsub(alpha, qs[k]);
-      if (k < nchild) S = fadd(S, fdiv(tops[k], bot[k]));
+    for (int k = 0; k < A; k++) { bot[k] = fsub(alpha, qs[k]); bmin = fminf(bmin, bot[k]); bmax = fmaxf(bmax, bot[k]); }
+    const bool fast = num_ok && bmin >= SQ_LO && bmax <= SQ_HI;                      // (a NaN denominator fails the comparison chain below)
+    float S;
+    if (fast) {
+      // all quotients first — independent, branch-free, overlapping in the pipeline — then the adds in reference order
+      S = fdiv_fast(rem, alpha);
+#pragma unroll
+      for (int k = 0; k < A; k++) t1[k] = fdiv_fast(tops[k], bot[k]);
+#pragma unroll
+      for (int k = 0; k < A; k++) if (k < nchild) S = fadd(S, t1[k]);
+    } else {
+      S = fdiv(rem, alpha);
+#pragma unroll
+      for (int k = 0; k < A; k++) if (k < nchild) S = fadd(S, fdiv(tops[k], bot[k]));
     }
     const float newerr = fsub(S, 1.f);
     if (newerr < 0.001f || newerr == err) break;
     // the derivative is only needed when the iteration continues (the reference computes it in the same loop and drops it on exit)
-    float gs = fdiv(-rem, fmul(alpha, alpha));
+    if (fast && alpha == alpha) {
+      float G = fdiv_fast(rem, fmul(alpha, alpha));
 #pragma unroll
-    for (int k = 0; k < A; k++)
-      if (k < nchild) gs = fadd(gs, fdiv(-tops[k], fmul(bot[k], bot[k])));
-    alpha = fsub(alpha, fdiv(newerr, gs));
+      for (int k = 0; k < A; k++) t1[k] = fdiv_fast(tops[k], fmul(bot[k], bot[k]));
+#pragma unroll
+      for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, t1[k]);
+      alpha = fadd(alpha, fdiv(newerr, G));
+    } else {
+      float gs = fdiv(-rem, fmul(alpha, alpha));
+#pragma unroll
+      for (int k = 0; k < A; k++) if (k < nchild) gs = fadd(gs, fdiv(-tops[k], fmul(bot[k], bot[k])));
+      alpha = fsub(alpha, fdiv(newerr, gs));
+    }
     err = newerr;
   }
+  {
+    float den[AP];
+    bool ok = true;
 #pragma unroll
-  for (int a = 0; a < A; a++) pol[a] = fdiv(top[a], fsub(alpha, q[a]));              // :165-169
+    for (int a = 0; a < A; a++) { den[a] = fsub(alpha, q[a]); ok = ok && fdiv_box_den(den[a]) && fdiv_box_num(top[a]); }
+    if (ok) {
+#pragma unroll
+      for (int a = 0; a < A; a++) pol[a] = fdiv_fast(top[a], den[a]);                  // :165-169
+    } else {
+#pragma unroll
+      for (int a = 0; a < A; a++) pol[a] = fdiv(top[a], den[a]);
+    }
+  }
 #pragma unroll
   for (int a = A; a < AP; a++) pol[a] = 0.f;
 }
@@ -560,6 +597,166 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FAST layouts, ONE THREAD per game (the fused per-ply kernel): with π̄ stored in the node the descent only samples, and almost
+// everything a lane group did was the same scalar work repeated on every lane (header decode, Philox, move generation for the new
+// node) — measured on B200 the 8-lane descent of 223 games kept an SM's issue slots busy for 28 k cycles per rollout.  One thread
+// per game issues an eighth of the instructions; the seven-term prefix scan it serialises is shorter than the shuffles it replaces.
+// Same operations in the same order as select_game / expand_game: results are bit-identical.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last_rollout, u64 seed, u32 ply) {
+  typedef Layout<G> Lay;
+  static_assert(Lay::FAST, "thread-per-game descent needs the stored policy");
+  constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
+  char* gbase = P.tree + (size_t)g * P.game_stride;
+  int nn = P.nnodes[g];
+  const u32 uid = P.uid[g];
+  int node = 0, depth = 0, rblock = -1;
+  Philox4 rnd; rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
+  uint8_t* pnode = P.path_node + (size_t)g * P.R;
+  uint8_t* pmove = P.path_move + (size_t)g * P.R;
+
+  while (true) {
+    char* rec = gbase + (size_t)node * REC;
+    // header, child ids and π̄ are the record's first bytes: every load of the level is issued before the flag is tested
+    const uint2 hw = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
+    uint32_t cw[AP / 4];
+#pragma unroll
+    for (int c = 0; c < AP / 8; c++) {
+      const uint2 cv = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8 * c);
+      cw[2 * c] = cv.x; cw[2 * c + 1] = cv.y;
+    }
+    float pol[AP];
+#pragma unroll
+    for (int c = 0; c < AP / 4; c++) {
+      const float4 pv = *reinterpret_cast<const float4*>(rec + Lay::OFF_POLICY + 16 * c);
+      pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
+    }
+    const int nchild = (int)((hw.x >> 16) & 0xFFu), flags = (int)(hw.x >> 24);
+    if (!(flags & F_EXPANDED)) break;                                                 // while expanded[nindex]==1  (:110)
+    if (node == 0 && last_rollout) {                                                  // copy_pol (:330-339)
+#pragma unroll
+      for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pol[a];
+    }
+    if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
+    const int w = depth & 3;
+    const float u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
+    // inverse-CDF scan in ascending action order (:172-182)
+    float cum = 0.f;
+    int best = -1;
+    bool done = false;
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      const float d = pol[a];
+      if (!done) {
+        cum = fadd(cum, d);
+        if (d > 0.f) best = a;
+        if (cum >= u) done = true;
+      }
+    }
+    if (best < 0) best = 0;
+    pnode[depth] = (uint8_t)node;
+    pmove[depth] = (uint8_t)best;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < AP / 4; k++) if ((best >> 2) == k) c = (int)((cw[k] >> (8 * (best & 3))) & 0xFFu);
+    if (c == 0) {                                                                     // allocate the child (:183-191)
+      nn += 1;
+      c = nn;
+      *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
+      *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
+      reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
+      const typename G::State ps = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+      const typename G::State ns = G::play(ps, best + 1);
+      int res = 0;
+      const bool term = G::is_over(ns, res);
+      char* nrec = gbase + (size_t)(c - 1) * REC;
+#pragma unroll
+      for (int k = 0; k < AP / 4; k++) *reinterpret_cast<float4*>(nrec + Lay::OFF_Q + 16 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < AP / 8; k++) {
+        *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
+      }
+      *reinterpret_cast<typename G::State*>(nrec + Lay::OFF_STATE) = ns;
+      NodeHdr nh; nh.parent = (uint8_t)(node + 1); nh.action = (uint8_t)(best + 1); nh.nchild = 0;
+      nh.flags = term ? F_TERMINAL : 0; nh.result = (int8_t)res; nh.pad[0] = nh.pad[1] = nh.pad[2] = 0;
+      *reinterpret_cast<NodeHdr*>(nrec + Lay::OFF_HDR) = nh;
+      node = c - 1;
+      depth += 1;
+      break;
+    }
+    node = c - 1;                                                                      // :192
+    depth += 1;
+  }
+  P.leaf[g] = node;                                                                    // :195
+  P.nnodes[g] = nn;
+  P.path_len[g] = (uint8_t)depth;
+  if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)depth); atomicAdd(&P.counters[1], 1ull); }
+}
+
+template <class G>
+AG_D LeafEval expand_game1(const SearchParams& P, const int g, int training, int last_rollout) {
+  typedef Layout<G> Lay;
+  static_assert(Lay::FAST, "thread-per-game expand is written for the FAST record");
+  constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
+  const int leaf = P.leaf[g];
+  char* rec = P.tree + (size_t)g * P.game_stride + (size_t)leaf * REC;
+  const NodeHdr h = *reinterpret_cast<const NodeHdr*>(rec + Lay::OFF_HDR);
+  const typename G::State st = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+  const bool term = (h.flags & F_TERMINAL) != 0;
+  float v = 0.f;
+  if (!term) {                                                                         // expand: :258-296, softmax! :417
+    float x[Lay::OUTS];
+#pragma unroll
+    for (int c = 0; c < Lay::OUTS / 4; c++) {
+      const float4 ov = *reinterpret_cast<const float4*>(P.nn_out + (size_t)g * Lay::OUTS + 4 * c);
+      x[4 * c] = ov.x; x[4 * c + 1] = ov.y; x[4 * c + 2] = ov.z; x[4 * c + 3] = ov.w;
+    }
+    v = x[A];
+    float m = -__int_as_float(0x7f800000);
+#pragma unroll
+    for (int a = 0; a < A; a++) m = fmaxf(m, x[a]);
+    float e[A], ssum = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; a++) { e[a] = c_expf(fsub(x[a], m)); ssum = fadd(ssum, e[a]); }
+    float normalize = 0.f;
+    int acount = 0;
+    bool legal[A];
+#pragma unroll
+    for (int a = 0; a < A; a++) {
+      e[a] = fdiv(e[a], ssum);
+      legal[a] = G::can_play(st, a + 1);
+      normalize = fadd(normalize, legal[a] ? e[a] : 0.f);
+      acount += legal[a] ? 1 : 0;
+    }
+    const bool rootmix = (leaf == 0) && training;                                       // :259-275
+    const float unif = fdiv(0.25f, (float)acount);
+    float pr[AP];
+#pragma unroll
+    for (int a = 0; a < AP; a++) pr[a] = 0.f;
+#pragma unroll
+    for (int a = 0; a < A; a++)
+      if (legal[a]) pr[a] = rootmix ? fadd(fdiv(fmul(0.75f, e[a]), normalize), unif) : fdiv(e[a], normalize);
+#pragma unroll
+    for (int c = 0; c < AP / 4; c++) {
+      const float4 pv = make_float4(pr[4 * c], pr[4 * c + 1], pr[4 * c + 2], pr[4 * c + 3]);
+      *reinterpret_cast<float4*>(rec + Lay::OFF_PRIOR + 16 * c) = pv;
+      *reinterpret_cast<float4*>(rec + Lay::OFF_POLICY + 16 * c) = pv;                 // policy[:,leaf] = prior[:,leaf]  (:297-299)
+    }
+    if (leaf == 0 && last_rollout) {
+#pragma unroll
+      for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pr[a];
+    }
+    reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
+  }
+  LeafEval E;
+  E.v = v; E.term = term ? 1 : 0; E.parent = h.parent; E.action = h.action;
+  E.value0_d = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;
+  return E;
 }
 
 template <class G, bool INJECT>

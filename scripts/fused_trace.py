@@ -12,12 +12,14 @@ for L in [int(x) for x in sys.argv[1:]] or [32768, 8192, 1024, 128]:
     ctx.set_weights(net)
     ctx.re_init(ctx.Position(L))
     ctx.mcts_single(64, cpuct=1.5, seed=1)
-    buf = torch.zeros(4 * 512, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(8 * 512, dtype=torch.int64, device="cuda")
     lib.agpu_debug_tc_trace(C.c_void_p(buf.data_ptr()))
     ctx.re_init(ctx.Position(L))
     ctx.mcts_single(64, cpuct=1.5, seed=2)
     lib.agpu_debug_tc_trace(None)
-    t = buf.cpu().numpy().reshape(-1, 4)
-    t = t[t[:, 3] > 0]
-    print(f"L={L}: CTAs {len(t)} games/CTA {t[:,2].mean():.0f}  per rollout: search {t[:,0].mean()/64:.0f} cyc ({t[:,0].mean()/64/1.965e3:.1f} us)  nn {t[:,1].mean()/64:.0f} cyc ({t[:,1].mean()/64/1.965e3:.1f} us)  max search {t[:,0].max()/64:.0f} max nn {t[:,1].max()/64:.0f}")
+    t = buf.cpu().numpy().reshape(-1, 8)
+    t = t[t[:, 6] > 0]
+    ph = t[:, :5].mean(0) / 64
+    print(f"L={L}: CTAs {len(t)} games/CTA {t[:,5].mean():.0f}  cycles per rollout: expand {ph[0]:.0f} scan {ph[1]:.0f} backup {ph[2]:.0f} select {ph[3]:.0f} "
+          f"network {ph[4]:.0f}  total {ph.sum():.0f} ({ph.sum()/1.965e3:.1f} us)")
     ctx.close()

@@ -234,3 +234,15 @@ def test_error_paths():
     with pytest.raises(ag._lib.AlphaGPUError):
         ag.Context(ag.GameSpec.named("connect4"), 300, 16, 128, 2)        # rollouts > 255
     ctx.close()
+
+
+def test_fdiv_fast_matches_ieee_division():
+    """The branch-free division of the α-solve (common.cuh: fdiv_fast) equals __fdiv_rn bit for bit on every operand pair it does not
+    flag, over 2^30 random pairs drawn in and around its exponent box (2^34 in profiles/r01_fdiv_check.txt)."""
+    import ctypes as C
+    from alphagpu_b200 import _lib
+    out = (C.c_uint64 * 2)()
+    assert _lib.load().agpu_debug_fdiv_check(1 << 30, 12345, out) == 0
+    mism, flagged = int(out[0]), int(out[1])
+    assert mism == 0
+    assert 0.05 * (1 << 30) < flagged < 0.4 * (1 << 30)      # the out-of-box band is exercised, the box is not empty
