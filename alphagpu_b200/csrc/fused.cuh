@@ -157,13 +157,13 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       for (int i = threadIdx.x; i < items; i += C::THREADS) {
         int lo = 0, hi = C::GAMES;                                     // largest gl with s_off[gl] <= i
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
-        backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct);
+        backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
       }
       __syncthreads();
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // (d) descent of this rollout
-    if (threadIdx.x < count) select_game1<G>(P, S.off + cta_first + (int)threadIdx.x, k, last, S.seed, S.ply);
+    if (threadIdx.x < count) select_game1<G>(P, S.off + cta_first + (int)threadIdx.x, k, last, S.seed, S.ply, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
     __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
@@ -280,8 +280,8 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
   if (T.dbg && threadIdx.x == 0) {
-    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 8 + i] = t_ph[i];
-    T.dbg[blockIdx.x * 8 + 5] = count; T.dbg[blockIdx.x * 8 + 6] = visits;
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 32 + i] = t_ph[i];
+    T.dbg[blockIdx.x * 32 + 5] = count; T.dbg[blockIdx.x * 32 + 6] = visits;
   }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
 // ------------------------------------------------------------------------------------------------
 template <int A, int AP>
 AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis)[AP], const int (&ch)[AP], const int (&ord)[AP],
-                     const int nchild, const float cpuct, float (&pol)[AP], const char* q_rec, const char* prior_rec) {
+                     const int nchild, const float cpuct, float (&pol)[AP], const char* q_rec, const char* prior_rec, long long* tr = nullptr) {
   int nv = 0, acount = 0;
   float rem = 0.f;
 #pragma unroll
@@ -178,12 +178,9 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
   const float n = (float)(1 + nv);
   const float lambda = fdiv(fmul(cpuct, fsqrt(n)), fadd((float)acount, n));      // :132
   rem = fmul(rem, lambda);                                                          // :134
-  float alpha = 0.f, top[AP];
+  float alpha = 0.f;
 #pragma unroll
-  for (int a = 0; a < A; a++) {
-    top[a] = fmul(lambda, p[a]);
-    alpha = fmaxf(alpha, fadd(q[a], fmaxf(top[a], 1e-4f)));                          // :135-138
-  }
+  for (int a = 0; a < A; a++) alpha = fmaxf(alpha, fadd(q[a], fmaxf(fmul(lambda, p[a]), 1e-4f)));   // :135-138
   // statistics of the children in slot (creation) order, gathered from the record by address — the caller has already stored
   // the updated q there — instead of 2*A*A register selects
   float tops[AP], qs[AP];
@@ -204,20 +201,24 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
 #pragma unroll
   for (int k = 0; k < A; k++) num_ok = num_ok && fdiv_box_num(tops[k]);
   float err = __int_as_float(0x7f800000);
+  const long long trs = tr ? clock64() + (__float_as_int(alpha) & 0) + (__float_as_int(tops[0]) & 0) + (__float_as_int(qs[A - 1]) & 0): 0;
   for (int it = 0; it < 100; it++) {                                                 // :141-162
-    float bot[AP], t1[AP];
+    float bot[AP];
     float bmin = alpha, bmax = alpha;
 #pragma unroll
     for (int k = 0; k < A; k++) { bot[k] = fsub(alpha, qs[k]); bmin = fminf(bmin, bot[k]); bmax = fmaxf(bmax, bot[k]); }
     const bool fast = num_ok && bmin >= SQ_LO && bmax <= SQ_HI;                      // (a NaN denominator fails the comparison chain below)
     float S;
     if (fast) {
-      // all quotients first — independent, branch-free, overlapping in the pipeline — then the adds in reference order
-      S = fdiv_fast(rem, alpha);
+      // all quotients first — independent, branch-free, staged so that they overlap in the pipeline — then the adds in reference order
+      float na[A + 1], nb[A + 1], nq[A + 1];
+      na[0] = rem; nb[0] = alpha;
 #pragma unroll
-      for (int k = 0; k < A; k++) t1[k] = fdiv_fast(tops[k], bot[k]);
+      for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = bot[k]; }
+      fdiv_fast_n<A + 1>(na, nb, nq);
+      S = nq[0];
 #pragma unroll
-      for (int k = 0; k < A; k++) if (k < nchild) S = fadd(S, t1[k]);
+      for (int k = 0; k < A; k++) if (k < nchild) S = fadd(S, nq[k + 1]);
     } else {
       S = fdiv(rem, alpha);
 #pragma unroll
@@ -227,11 +228,14 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
     if (newerr < 0.001f || newerr == err) break;
     // the derivative is only needed when the iteration continues (the reference computes it in the same loop and drops it on exit)
     if (fast && alpha == alpha) {
-      float G = fdiv_fast(rem, fmul(alpha, alpha));
+      float na[A + 1], nb[A + 1], nq[A + 1];
+      na[0] = rem; nb[0] = fmul(alpha, alpha);
 #pragma unroll
-      for (int k = 0; k < A; k++) t1[k] = fdiv_fast(tops[k], fmul(bot[k], bot[k]));
+      for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = fmul(bot[k], bot[k]); }
+      fdiv_fast_n<A + 1>(na, nb, nq);
+      float G = nq[0];
 #pragma unroll
-      for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, t1[k]);
+      for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[k + 1]);
       alpha = fadd(alpha, fdiv(newerr, G));
     } else {
       float gs = fdiv(-rem, fmul(alpha, alpha));
@@ -241,17 +245,31 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
     }
     err = newerr;
   }
+  if (tr) tr[3] += clock64() + (__float_as_int(alpha) & 0) - trs;
   {
-    float den[AP];
+    // π̄_a = λ p_a / (α - q_a) (:165-169).  p and q are read again from the record (first-level cache) rather than kept in registers
+    // across the Newton loop: at the kernel's 64-register cap the loop needs them for overlapping its divisions.
+    float num[A], den[A];
     bool ok = true;
 #pragma unroll
-    for (int a = 0; a < A; a++) { den[a] = fsub(alpha, q[a]); ok = ok && fdiv_box_den(den[a]) && fdiv_box_num(top[a]); }
-    if (ok) {
+    for (int c = 0; c < AP / 4; c++) {
+      float pv[4], qv[4];
+      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv[0]), "=f"(pv[1]), "=f"(pv[2]), "=f"(pv[3]) : "l"(prior_rec + 16 * c) : "memory");
+      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(qv[0]), "=f"(qv[1]), "=f"(qv[2]), "=f"(qv[3]) : "l"(q_rec + 16 * c) : "memory");
 #pragma unroll
-      for (int a = 0; a < A; a++) pol[a] = fdiv_fast(top[a], den[a]);                  // :165-169
+      for (int e = 0; e < 4; e++) {
+        const int a = 4 * c + e;
+        if (a < A) { num[a] = fmul(lambda, pv[e]); den[a] = fsub(alpha, qv[e]); ok = ok && fdiv_box_den(den[a]) && fdiv_box_num(num[a]); }
+      }
+    }
+    if (ok) {
+      float nq[A];
+      fdiv_fast_n<A>(num, den, nq);
+#pragma unroll
+      for (int a = 0; a < A; a++) pol[a] = nq[a];
     } else {
 #pragma unroll
-      for (int a = 0; a < A; a++) pol[a] = fdiv(top[a], den[a]);
+      for (int a = 0; a < A; a++) pol[a] = fdiv(num[a], den[a]);
     }
   }
 #pragma unroll
@@ -530,7 +548,9 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // the value an ancestor receives is the leaf value flipped once per level below it (value = 1 - value, :324), evaluated as that
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
 template <class G>
-AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct) {
+AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
+                      long long* tr = nullptr) {
+  const long long tr0 = tr ? clock64() : 0;
   typedef Layout<G> Lay;
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
   char* gbase = P.tree + (size_t)g * P.game_stride;
@@ -588,8 +608,11 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
         for (int a = 0; a < A; a++) if (a == mv) { q[a] = qnew; vis[a] = vold + 1; }
         *reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * mv) = qnew;
         *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * mv) = (uint16_t)(vold + 1);
+        long long tr1 = 0;
+        if (tr) { tr1 = clock64() + (__float_as_int(qnew) & 0); tr[0] += tr1 - tr0; }
         if (!last_rollout) {
-          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol, nrec + Lay::OFF_Q, nrec + Lay::OFF_PRIOR);
+          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol, nrec + Lay::OFF_Q, nrec + Lay::OFF_PRIOR, tr);
+          if (tr) { tr[1] += clock64() + (__float_as_int(pol[0]) & 0) - tr1; tr[2] += 1; }
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
             *reinterpret_cast<float4*>(nrec + Lay::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
@@ -607,7 +630,9 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 // Same operations in the same order as select_game / expand_game: results are bit-identical.
 // ------------------------------------------------------------------------------------------------
 template <class G>
-AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last_rollout, u64 seed, u32 ply) {
+AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last_rollout, u64 seed, u32 ply, long long* tr = nullptr) {
+  const long long tr0 = tr ? clock64() : 0;
+  long long trA = tr0, trB = tr0, trC = tr0, trD = tr0;
   typedef Layout<G> Lay;
   static_assert(Lay::FAST, "thread-per-game descent needs the stored policy");
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
@@ -635,15 +660,18 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
       const float4 pv = *reinterpret_cast<const float4*>(rec + Lay::OFF_POLICY + 16 * c);
       pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
     }
+    // the uniform of this depth does not depend on the loads above: Philox runs while they are in flight
+    if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
+    const int w = depth & 3;
+    const float u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
     const int nchild = (int)((hw.x >> 16) & 0xFFu), flags = (int)(hw.x >> 24);
+    if (tr && depth == 0) trA = clock64() + (hw.x & 0) + (__float_as_int(pol[A - 1]) & 0) + (cw[0] & 0);
     if (!(flags & F_EXPANDED)) break;                                                 // while expanded[nindex]==1  (:110)
     if (node == 0 && last_rollout) {                                                  // copy_pol (:330-339)
 #pragma unroll
       for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pol[a];
     }
-    if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
-    const int w = depth & 3;
-    const float u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
+    if (tr && depth == 0) trB = clock64() + (__float_as_int(u) & 0);
     // inverse-CDF scan in ascending action order (:172-182)
     float cum = 0.f;
     int best = -1;
@@ -658,6 +686,7 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
       }
     }
     if (best < 0) best = 0;
+    if (tr && depth == 0) trC = clock64() + (best & 0);
     pnode[depth] = (uint8_t)node;
     pmove[depth] = (uint8_t)best;
     int c = 0;
@@ -691,7 +720,9 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
     }
     node = c - 1;                                                                      // :192
     depth += 1;
+    if (tr && depth == 1) trD = clock64() + (node & 0);
   }
+  if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }
   P.leaf[g] = node;                                                                    // :195
   P.nnodes[g] = nn;
   P.path_len[g] = (uint8_t)depth;

@@ -12,14 +12,19 @@ for L in [int(x) for x in sys.argv[1:]] or [32768, 8192, 1024, 128]:
     ctx.set_weights(net)
     ctx.re_init(ctx.Position(L))
     ctx.mcts_single(64, cpuct=1.5, seed=1)
-    buf = torch.zeros(8 * 512, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(32 * 512, dtype=torch.int64, device="cuda")
     lib.agpu_debug_tc_trace(C.c_void_p(buf.data_ptr()))
     ctx.re_init(ctx.Position(L))
     ctx.mcts_single(64, cpuct=1.5, seed=2)
     lib.agpu_debug_tc_trace(None)
-    t = buf.cpu().numpy().reshape(-1, 8)
+    t = buf.cpu().numpy().reshape(-1, 32)
     t = t[t[:, 6] > 0]
     ph = t[:, :5].mean(0) / 64
     print(f"L={L}: CTAs {len(t)} games/CTA {t[:,5].mean():.0f}  cycles per rollout: expand {ph[0]:.0f} scan {ph[1]:.0f} backup {ph[2]:.0f} select {ph[3]:.0f} "
           f"network {ph[4]:.0f}  total {ph.sum():.0f} ({ph.sum()/1.965e3:.1f} us)")
+    x = t[:, 8:].sum(0).astype(float)
+    if x[2] > 0:
+        print(f"      thread 0: backup item load+update {x[0]/x[2]:.0f} cyc, solve {x[1]/x[2]:.0f} cyc ({x[2]/len(t)/64:.2f} items/rollout); "
+              f"select total {x[4]/len(t)/64:.0f} cyc at warp-max depth, own depth {x[5]/len(t)/64:.2f}, first level {x[6]/len(t)/64:.0f} cyc; "
+              f"newton loop {x[3]/x[2]:.0f} cyc; select level 0: loads {x[8]/len(t)/64:.0f}, +philox {x[9]/len(t)/64:.0f}, +scan {x[10]/len(t)/64:.0f}")
     ctx.close()
