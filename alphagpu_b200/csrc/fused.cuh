@@ -26,7 +26,7 @@ template <int NT> struct FCfg {
   static constexpr int THREADS = 512 * NT;
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 10240;   // + alignment slack + barriers/bias/backup work list
+  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 1024 + GAMES * (44 + 72);   // + alignment slack + barriers/bias/backup work list + rollout hand-off
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
   static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
 };
@@ -67,6 +67,20 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   LeafEval* s_eval = reinterpret_cast<LeafEval*>(bars + 80);           // [256]
   int* s_d = reinterpret_cast<int*>(s_eval + C::GAMES);                // [256]
   int* s_off = s_d + C::GAMES;                                         // [257]
+  // hand-off between the phases of a rollout (search.cuh: RolloutShared), 128 bytes per game
+  RolloutShared<G> SH;
+  SH.state = reinterpret_cast<typename G::State*>((reinterpret_cast<uintptr_t>(s_off + C::GAMES + 1) + 15) & ~uintptr_t(15));   // 16-byte aligned (float4 reads of `out`)
+  SH.hdr = reinterpret_cast<NodeHdr*>(SH.state + C::GAMES);
+  SH.d = s_d;
+  SH.leaf = reinterpret_cast<uint8_t*>(SH.hdr + C::GAMES);
+  SH.pn = SH.leaf + C::GAMES;
+  SH.pm = SH.pn + C::GAMES * PATH_SMEM_DEPTH;
+  // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
+  // expand reads the outputs in between.  (Staying under 196 KB of shared memory keeps the next carve-out step — 32 KB of L1 — free.)
+  SH.out = reinterpret_cast<float*>(sA);
+  SH.out_tile_stride = TC_A_BYTES / 4;
+  static_assert(sizeof(typename G::State) + 8 + 1 + 2 * PATH_SMEM_DEPTH <= 68, "rollout hand-off budget per game");
+  static_assert(FCfg<2>::SMEM <= 195 * 1024, "shared memory beyond the 196 KB carve-out costs 32 KB of L1");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
@@ -116,6 +130,13 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   const bool issuer = (warp & 15) == 0 && lane == 0;
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
+  // one thread per game for the descent and the expansion: its uid and node count stay in registers for the whole ply
+  const bool has_game = (int)threadIdx.x < count;
+  const int my_g = S.off + cta_first + (int)threadIdx.x;
+  const u32 my_uid = has_game ? P.uid[my_g] : 0u;
+  int my_nn = has_game ? P.nnodes[my_g] : 0;
+  if (threadIdx.x < C::GAMES) s_d[threadIdx.x] = 0;
+
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
   long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): expand, scan, backup, select, network
   for (int k = 0; k < visits; k++) {
@@ -123,16 +144,7 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
     // ================= search phase =================
     if (k > 0) {
       // (a) expand every game of the CTA (softmax, legal mask, prior), leaving value and path length in shared memory
-      if (threadIdx.x < C::GAMES) {                                    // one thread per game (search.cuh: expand_game1)
-        const int gl = threadIdx.x;
-        const int g = S.off + cta_first + gl;
-        if (g < L_end) {
-          s_eval[gl] = expand_game1<G>(P, g, S.training, 0);
-          s_d[gl] = P.path_len[g];
-        } else {
-          s_d[gl] = 0;
-        }
-      }
+      if (has_game) s_eval[threadIdx.x] = expand_game1<G>(P, my_g, (int)threadIdx.x, SH, S.training, 0);   // one thread per game
       __syncthreads();
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[0] += c - t_mark; t_mark = c; }
       // (b) exclusive prefix sum of the path lengths (warp 0, GAMES/32 entries per lane)
@@ -157,13 +169,14 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       for (int i = threadIdx.x; i < items; i += C::THREADS) {
         int lo = 0, hi = C::GAMES;                                     // largest gl with s_off[gl] <= i
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
-        backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
+        backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
+                       SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH);
       }
       __syncthreads();
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // (d) descent of this rollout
-    if (threadIdx.x < count) select_game1<G>(P, S.off + cta_first + (int)threadIdx.x, k, last, S.seed, S.ply, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
+    if (has_game) select_game1<G>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
     __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
@@ -172,7 +185,7 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       // A operand of the base layer: this thread's 32 operand columns of its row (decoder, mcts_gpu.jl:202-223)
       uint32_t bits = 0;
       if (g_row < L_end) {
-        const u64* st = reinterpret_cast<const u64*>(P.tree + (size_t)g_row * P.game_stride + (size_t)P.leaf[g_row] * Lay::REC + Lay::OFF_STATE);
+        const u64* st = reinterpret_cast<const u64*>(SH.state + t * TC_TILE_M + r);     // left there by this rollout's descent
         const u64 bp = st[0], bo = st[1];
         constexpr int VS = G::VS;
         const u64 x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
@@ -267,9 +280,14 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
               for (int e = 0; e < 16; e++) if (a0 + e == T.A) z[e] = c_sigmoidf(z[e]);
             }
             if (g_row < L_end) {
+              float* so = SH.out + t * SH.out_tile_stride + r * Lay::OUTS;
 #pragma unroll
               for (int q4 = 0; q4 < 4; q4++)
-                if (a0 + 4 * q4 < Lay::OUTS) *reinterpret_cast<float4*>(o + a0 + 4 * q4) = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+                if (a0 + 4 * q4 < Lay::OUTS) {
+                  const float4 zv = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+                  *reinterpret_cast<float4*>(so + a0 + 4 * q4) = zv;
+                  *reinterpret_cast<float4*>(o + a0 + 4 * q4) = zv;
+                }
             }
           }
         }

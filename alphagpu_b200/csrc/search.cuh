@@ -102,6 +102,23 @@ struct SearchParams {
   uint8_t* path_len;     // [L]
 };
 
+// Shared-memory hand-off between the phases of one rollout inside the fused per-ply kernel: what one phase leaves for the next
+// (leaf node, its state and header, the path, the network's output) would otherwise make a round trip through L2 — about a
+// thousand cycles each on the serial chain descent -> encode -> network -> expand -> backup -> descent.  Global memory keeps a copy
+// of everything (the stores are off the critical path), so the stand-alone kernels and the read-back entry points see the same data.
+constexpr int PATH_SMEM_DEPTH = 16;          // path entries per game held in shared memory; deeper levels are read from global
+template <class G>
+struct RolloutShared {
+  typename G::State* state;  // [GAMES] state of the leaf
+  NodeHdr* hdr;              // [GAMES] header of the leaf as the descent saw it
+  float* out;                // logits, value of the leaf: row gl at out + (gl / 128) * out_tile_stride + (gl % 128) * OUTS
+  int out_tile_stride;       // (floats) the rows of a 128-game tile live in that tile's idle A-operand buffer
+  int* d;                    // [GAMES] path length
+  uint8_t* leaf;             // [GAMES]
+  uint8_t* pn;               // [GAMES][PATH_SMEM_DEPTH] path nodes
+  uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
+};
+
 // One independent slice of the live games.  The rollout loop of a slice is replayed from a CUDA graph on its own stream, so
 // everything that changes from ply to ply is read from this device-resident record instead of being a kernel argument.
 struct SegParams {
@@ -549,7 +566,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
 template <class G>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
-                      long long* tr = nullptr) {
+                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr) {
   const long long tr0 = tr ? clock64() : 0;
   typedef Layout<G> Lay;
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
@@ -561,8 +578,10 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
     {
       {
         const int flips = d - 1 - jj;
-        const int nd = P.path_node[(size_t)g * P.R + jj];
-        const int mv = P.path_move[(size_t)g * P.R + jj];
+        // s_pn / s_pm: this game's path in shared memory (fused kernel), PATH_SMEM_DEPTH entries
+        const bool in_smem = s_pn != nullptr && jj < PATH_SMEM_DEPTH;
+        const int nd = in_smem ? s_pn[jj] : P.path_node[(size_t)g * P.R + jj];
+        const int mv = in_smem ? s_pm[jj] : P.path_move[(size_t)g * P.R + jj];
         char* nrec = gbase + (size_t)nd * REC;
         float p[AP], q[AP], pol[AP];
         int vis[AP], ch[AP], ord[AP];
@@ -630,24 +649,24 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 // Same operations in the same order as select_game / expand_game: results are bit-identical.
 // ------------------------------------------------------------------------------------------------
 template <class G>
-AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last_rollout, u64 seed, u32 ply, long long* tr = nullptr) {
+AG_D void select_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, const u32 uid, int& nn, int rollout, int last_rollout,
+                       u64 seed, u32 ply, long long* tr = nullptr) {
   const long long tr0 = tr ? clock64() : 0;
   long long trA = tr0, trB = tr0, trC = tr0, trD = tr0;
   typedef Layout<G> Lay;
   static_assert(Lay::FAST, "thread-per-game descent needs the stored policy");
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
   char* gbase = P.tree + (size_t)g * P.game_stride;
-  int nn = P.nnodes[g];
-  const u32 uid = P.uid[g];
   int node = 0, depth = 0, rblock = -1;
   Philox4 rnd; rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
   uint8_t* pnode = P.path_node + (size_t)g * P.R;
   uint8_t* pmove = P.path_move + (size_t)g * P.R;
+  uint2 hw;
 
   while (true) {
     char* rec = gbase + (size_t)node * REC;
     // header, child ids and π̄ are the record's first bytes: every load of the level is issued before the flag is tested
-    const uint2 hw = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
+    hw = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
     uint32_t cw[AP / 4];
 #pragma unroll
     for (int c = 0; c < AP / 8; c++) {
@@ -666,7 +685,12 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
     const float u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
     const int nchild = (int)((hw.x >> 16) & 0xFFu), flags = (int)(hw.x >> 24);
     if (tr && depth == 0) trA = clock64() + (hw.x & 0) + (__float_as_int(pol[A - 1]) & 0) + (cw[0] & 0);
-    if (!(flags & F_EXPANDED)) break;                                                 // while expanded[nindex]==1  (:110)
+    if (!(flags & F_EXPANDED)) {                                                      // while expanded[nindex]==1  (:110)
+      // an existing node that is not expanded: the root before its first evaluation, or a terminal node
+      SH.state[gl] = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+      SH.hdr[gl] = *reinterpret_cast<const NodeHdr*>(&hw);
+      break;
+    }
     if (node == 0 && last_rollout) {                                                  // copy_pol (:330-339)
 #pragma unroll
       for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pol[a];
@@ -689,6 +713,7 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
     if (tr && depth == 0) trC = clock64() + (best & 0);
     pnode[depth] = (uint8_t)node;
     pmove[depth] = (uint8_t)best;
+    if (depth < PATH_SMEM_DEPTH) { SH.pn[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)node; SH.pm[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)best; }
     int c = 0;
 #pragma unroll
     for (int k = 0; k < AP / 4; k++) if ((best >> 2) == k) c = (int)((cw[k] >> (8 * (best & 3))) & 0xFFu);
@@ -714,6 +739,8 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
       NodeHdr nh; nh.parent = (uint8_t)(node + 1); nh.action = (uint8_t)(best + 1); nh.nchild = 0;
       nh.flags = term ? F_TERMINAL : 0; nh.result = (int8_t)res; nh.pad[0] = nh.pad[1] = nh.pad[2] = 0;
       *reinterpret_cast<NodeHdr*>(nrec + Lay::OFF_HDR) = nh;
+      SH.state[gl] = ns;
+      SH.hdr[gl] = nh;
       node = c - 1;
       depth += 1;
       break;
@@ -723,6 +750,8 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
     if (tr && depth == 1) trD = clock64() + (node & 0);
   }
   if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }
+  SH.leaf[gl] = (uint8_t)node;
+  SH.d[gl] = depth;
   P.leaf[g] = node;                                                                    // :195
   P.nnodes[g] = nn;
   P.path_len[g] = (uint8_t)depth;
@@ -730,21 +759,21 @@ AG_D void select_game1(const SearchParams& P, const int g, int rollout, int last
 }
 
 template <class G>
-AG_D LeafEval expand_game1(const SearchParams& P, const int g, int training, int last_rollout) {
+AG_D LeafEval expand_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, int training, int last_rollout) {
   typedef Layout<G> Lay;
   static_assert(Lay::FAST, "thread-per-game expand is written for the FAST record");
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
-  const int leaf = P.leaf[g];
+  const int leaf = SH.leaf[gl];
   char* rec = P.tree + (size_t)g * P.game_stride + (size_t)leaf * REC;
-  const NodeHdr h = *reinterpret_cast<const NodeHdr*>(rec + Lay::OFF_HDR);
-  const typename G::State st = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+  const NodeHdr h = SH.hdr[gl];
+  const typename G::State st = SH.state[gl];
   const bool term = (h.flags & F_TERMINAL) != 0;
   float v = 0.f;
   if (!term) {                                                                         // expand: :258-296, softmax! :417
     float x[Lay::OUTS];
 #pragma unroll
     for (int c = 0; c < Lay::OUTS / 4; c++) {
-      const float4 ov = *reinterpret_cast<const float4*>(P.nn_out + (size_t)g * Lay::OUTS + 4 * c);
+      const float4 ov = *reinterpret_cast<const float4*>(SH.out + (gl >> 7) * SH.out_tile_stride + (gl & 127) * Lay::OUTS + 4 * c);
       x[4 * c] = ov.x; x[4 * c + 1] = ov.y; x[4 * c + 2] = ov.z; x[4 * c + 3] = ov.w;
     }
     v = x[A];
