@@ -227,8 +227,10 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
         umma_commit(bar_done + 8 * t);
         umma_commit(bar_empty + 8 * s);
         if (wl == 0 && t == 0) umma_commit(bar_stagger);
-        if (t == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
       }
+      // the weights two layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the issuer
+      // the request sat on the critical path: 2 k cycles per rollout)
+      if (warp == 1 && lane == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
       mbar_wait(bar_done + 8 * t, wl & 1);
       tc_fence_after();
 

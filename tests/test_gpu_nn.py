@@ -126,11 +126,13 @@ def test_tc_selfplay_properties_full_size():
     ctx.close()
 
 
-@pytest.mark.parametrize("name,games,R", [("connect4", 3000, 24), ("ttt", 1500, 16), ("connect4", 40000, 8)])
+@pytest.mark.parametrize("name,games,R", [("connect4", 3000, 24), ("ttt", 1500, 16), ("connect4", 40000, 8),
+                                          ("connect4", 1, 1), ("connect4", 257, 2), ("connect4", 300, 255), ("ttt", 33, 200)])
 def test_fused_ply_kernel_equals_separate_kernels(monkeypatch, name, games, R):
     """The persistent per-ply kernel (fused.cuh) and the per-rollout kernels (search.cuh + nn_tc.cu) run the same device functions
     and the same MMA sequence: a whole self-play generation must come out identical, bit for bit.  Game counts that are not
-    multiples of 256 exercise partially filled tiles and CTAs; 40000 games exceed one CTA per SM (full 256-game CTAs)."""
+    multiples of 256 exercise partially filled tiles and CTAs; 40000 games exceed one CTA per SM (full 256-game CTAs); one game with
+    one rollout, and the maximum rollout count (node ids are bytes) with paths deeper than the 16 levels kept in shared memory."""
     pnet, _ = make_nets(GAME_SPECS[name], 128, 6, seed=11)
     outs = []
     for fused in ("1", "0"):
@@ -142,7 +144,8 @@ def test_fused_ply_kernel_equals_separate_kernels(monkeypatch, name, games, R):
         ctx.close()
     (r1, s1, a), (r0, s0, b) = outs
     assert np.array_equal(r1, r0) and s1["positions"] == s0["positions"] and s1["faults"] == 0
-    assert s1["kernel_launches"] < s0["kernel_launches"] / 10
+    if R >= 8:
+        assert s1["kernel_launches"] < s0["kernel_launches"] / 10
     for k in a:
         if a[k].dtype.kind == "f":
             assert np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
