@@ -134,6 +134,8 @@ struct EngineT : EngineBase {
   // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
   static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;   // and width 128, checked at run time
   bool use_fused = false;
+  bool fused_swap = true;
+  int fused_swap_max = 128;        // games per CTA up to which the 512-thread variant is launched
   int num_sms = 148, fused_min_gpc = 32, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
   // profiling
   bool profiling = false;
@@ -241,7 +243,11 @@ struct EngineT : EngineBase {
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         if (const char* e = getenv("AGPU_FUSED_TILES")) fused_tiles = atoi(e) == 2 ? 2 : 1;
+        if (const char* e = getenv("AGPU_FUSED_SWAP")) fused_swap = atoi(e) != 0;
+        if (const char* e = getenv("AGPU_FUSED_SWAP_MAX")) fused_swap_max = atoi(e);
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
@@ -272,7 +278,11 @@ struct EngineT : EngineBase {
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (fused_tiles == 1) {
+        if (gpc <= fused_swap_max && fused_swap) {
+          // the tail of a generation: few games per CTA -> the 512-thread, 128-register, swapped-orientation variant
+          if (fmt == 0) fused::ply_kernel<G, 0, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
+        } else if (fused_tiles == 1) {
           if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
         } else {

@@ -39,9 +39,55 @@ AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
       : "memory");
 }
 AG_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+AG_D void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+AG_D void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+AG_D void tmem_ldn(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
+AG_D void tmem_ldn(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
+AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[8]) { tmem_st8(taddr, v); }
+AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
 
-template <class G, int FMT, int NT>
-__global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+// Epilogue of a trunk layer computed in the SWAPPED orientation (few games per CTA): the accumulator holds out-feature f in TMEM
+// lane f and game n in column n.  This thread owns feature 32*wq + lane and the NC games of slice cs; it applies relu / the
+// residual, keeps the fp32 stream in TMEM (same transposed shape) and scatters the 16-bit operand of the next layer into the
+// ordinary games x features, K-major, 128B-swizzled tile (so the head layer and the encoder need no second layout).
+template <int FMT, int NC>
+AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs, int lane, int l, bool keep, unsigned char* At) {
+  uint32_t va[NC], vh[NC];
+  const uint32_t taddr = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * NC);
+  tmem_ldn(tmem_acc + taddr, va);
+  if (l > 0) tmem_ldn(tmem_res + taddr, vh);
+  tmem_ld_wait();
+#pragma unroll
+  for (int e = 0; e < NC; e++) {
+    const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
+    const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
+    vh[e] = __float_as_uint(hv);
+  }
+  if (keep) tmem_stn(tmem_res + taddr, vh);
+  const int f = 32 * wq + lane;
+  unsigned char* base = At + (f >> 6) * TC_KTILE_BYTES_A + (f & 7) * 2;
+  const int c = (f & 63) >> 3;
+#pragma unroll
+  for (int e = 0; e < NC; e++) {
+    const int n = cs * NC + e;
+    *reinterpret_cast<uint16_t*>(base + n * 128 + ((c ^ (n & 7)) << 4)) = (uint16_t)(pack2<FMT>(__uint_as_float(vh[e]), 0.f) & 0xFFFFu);
+  }
+}
+
+
+// SW: the small-batch variant (host: games per CTA <= 128): one tile, 512 threads, one CTA per SM — 128 registers per thread instead
+// of 64 — and, up to 64 games, the trunk layers in the swapped orientation (below).
+template <class G, int FMT, int NT, bool SW = false>
+__global__ void __launch_bounds__(FCfg<NT>::THREADS, SW ? 1 : FCfg<NT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+  static_assert(!SW || NT == 1, "the swapped variant runs a single tile");
   typedef Layout<G> Lay;
   typedef FCfg<NT> C;
   constexpr int W = Lay::W;
@@ -54,6 +100,11 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
   const int count = min(gpc, S.len - cta_first);                       // games of this CTA
   const int L_end = S.off + cta_first + count;                         // one past this CTA's last slot
   const int ntiles = (NT == 2 && count > TC_TILE_M) ? 2 : 1;           // a CTA with <= 128 games runs a single tile
+  // Few games per CTA (the long tail of a generation): the trunk layers run as D^T = W * X^T — out-features on the M = 128 side, the
+  // NS = 32 / 64 games on the N side — so the tensor time and the epilogue shrink with the batch instead of paying for 128 rows.
+  // The weight image (out x in, K-major) serves as the A operand unchanged and the activation tile as the B operand unchanged.
+  const bool swapped = SW && count <= 64;                              // CTA-uniform; 65..128 games keep the ordinary orientation
+  const int NS = count <= 32 ? 32 : 64;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -216,13 +267,23 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
         tc_fence_after();
         const uint64_t ad0 = umma_desc(smem_u32(At));
         const uint64_t bd0 = umma_desc(smem_u32(sW + s * TC_W_STAGE_BYTES));
-        const uint32_t idesc = umma_idesc<FMT>(nl);
         const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
+        if (SW && swapped && !is_head) {
+          const uint32_t idesc = umma_idesc<FMT>(NS);                   // M = 128 out-features, N = NS games
 #pragma unroll
-        for (int ks = 0; ks < TC_N / 16; ks++) {
-          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-          umma_bf16(tmem_acc, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < TC_N / 16; ks++) {
+            const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+            const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+            umma_bf16(tmem_acc, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
+          }
+        } else {
+          const uint32_t idesc = umma_idesc<FMT>(nl);
+#pragma unroll
+          for (int ks = 0; ks < TC_N / 16; ks++) {
+            const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+            const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+            umma_bf16(tmem_acc, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+          }
         }
         umma_commit(bar_done + 8 * t);
         umma_commit(bar_empty + 8 * s);
@@ -234,7 +295,17 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, FCfg<NT>::CTAS_PER_SM) ply_
       mbar_wait(bar_done + 8 * t, wl & 1);
       tc_fence_after();
 
-      if (!is_head) {
+      if (SW && swapped && !is_head) {
+        const bool keep = (l + 2 < nlayers);
+        if constexpr (SW) {
+          if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, tmem_res, wq, cs, lane, l, keep, At);
+          else epilogue_swapped<FMT, 16>(tmem_acc, tmem_res, wq, cs, lane, l, keep, At);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        fence_proxy_async();
+        named_bar_sync(1 + t, 512);
+      } else if (!is_head) {
         // epilogue: b = relu(acc) (base) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b)
         const bool keep = (l + 2 < nlayers);                            // the last trunk layer's residual is not read again
 #pragma unroll
