@@ -135,6 +135,7 @@ struct EngineT : EngineBase {
   static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;   // and width 128, checked at run time
   bool use_fused = false;
   bool fused_swap = true;
+  int fused_wpt = 8;               // warps per tile of the two-tile variant: 8 = 512 threads x 128 registers (16: 1024 x 64, 91 vs 84 ms)
   int fused_swap_max = 128;        // games per CTA up to which the 512-thread variant is launched
   int num_sms = 148, fused_min_gpc = 32, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
   // profiling
@@ -246,6 +247,9 @@ struct EngineT : EngineBase {
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         if (const char* e = getenv("AGPU_FUSED_TILES")) fused_tiles = atoi(e) == 2 ? 2 : 1;
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
+        if (const char* e = getenv("AGPU_FUSED_WPT")) fused_wpt = atoi(e) == 8 ? 8 : 16;
         if (const char* e = getenv("AGPU_FUSED_SWAP")) fused_swap = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_SWAP_MAX")) fused_swap_max = atoi(e);
         use_fused = true;
@@ -282,6 +286,10 @@ struct EngineT : EngineBase {
           // the tail of a generation: few games per CTA -> the 512-thread, 128-register, swapped-orientation variant
           if (fmt == 0) fused::ply_kernel<G, 0, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
+        } else if (fused_wpt == 8 && fused_tiles == 2) {
+          // two tiles, 8 warps per tile: 512 threads with 128 registers each
+          if (fmt == 0) fused::ply_kernel<G, 0, 2, false, 8><<<grid, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 2, false, 8><<<grid, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
         } else if (fused_tiles == 1) {
           if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);

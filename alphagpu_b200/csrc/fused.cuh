@@ -22,8 +22,8 @@ using namespace tc;
 // NT = tiles per CTA.  NT = 2: 1024 threads, one CTA per SM, 3-stage weight ring.  NT = 1: 512 threads, 2-stage ring, TWO CTAs per
 // SM (98 KB shared memory, 256 TMEM columns, 64 registers each): while one CTA waits on its MMA chain the other's search phase
 // uses the issue slots.
-template <int NT> struct FCfg {
-  static constexpr int THREADS = 512 * NT;
+template <int NT, int WPT = 16> struct FCfg {
+  static constexpr int THREADS = 32 * WPT * NT;                        // WPT warps per tile: 16 (one 32-column slice per warp) or 8 (two)
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 1024 + GAMES * (44 + 72);   // + alignment slack + barriers/bias/backup work list + rollout hand-off
@@ -85,11 +85,13 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs,
 
 // SW: the small-batch variant (host: games per CTA <= 128): one tile, 512 threads, one CTA per SM — 128 registers per thread instead
 // of 64 — and, up to 64 games, the trunk layers in the swapped orientation (below).
-template <class G, int FMT, int NT, bool SW = false>
-__global__ void __launch_bounds__(FCfg<NT>::THREADS, SW ? 1 : FCfg<NT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
-  static_assert(!SW || NT == 1, "the swapped variant runs a single tile");
+template <class G, int FMT, int NT, bool SW = false, int WPT = 16>
+__global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 : FCfg<NT, WPT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+  static_assert(!SW || (NT == 1 && WPT == 16), "the swapped variant runs a single tile with 16 warps");
+  static_assert(WPT == 16 || WPT == 8, "warps per tile");
   typedef Layout<G> Lay;
-  typedef FCfg<NT> C;
+  typedef FCfg<NT, WPT> C;
+  constexpr int CPW = 16 / WPT;                                        // 32-column slices per warp
   constexpr int W = Lay::W;
   constexpr int STAGES = C::STAGES;
   static_assert(Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= TC_N, "fused ply kernel: small boards only");
@@ -171,14 +173,14 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, SW ? 1 : FCfg<NT>::CTAS_PER
   constexpr int GROUPS = C::THREADS / W;                               // games per pass
   constexpr int PASSES = C::GAMES / GROUPS;
   // network: tile, TMEM lane quarter, 32-column slice
-  const int t = warp >> 4, wq = warp & 3, cs = (warp >> 2) & 3;
+  const int t = warp / WPT, wq = warp & 3, csb = ((warp >> 2) & (WPT / 4 - 1)) * CPW;   // first column slice of this warp
   const int r = wq * 32 + lane;
   const int g_row = S.off + cta_first + t * TC_TILE_M + r;            // the game whose activations this thread carries
   unsigned char* At = sA + t * TC_A_BYTES;
   const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
   const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
-  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
-  const bool issuer = (warp & 15) == 0 && lane == 0;
+  const uint32_t lane_row = (uint32_t)(wq * 32) << 16;
+  const bool issuer = (warp % WPT) == 0 && lane == 0;
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
   // one thread per game for the descent and the expansion: its uid and node count stay in registers for the whole ply
@@ -234,28 +236,32 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, SW ? 1 : FCfg<NT>::CTAS_PER
     // ================= network phase =================
     {
       // A operand of the base layer: this thread's 32 operand columns of its row (decoder, mcts_gpu.jl:202-223)
-      uint32_t bits = 0;
+      u64 x0 = 0, x1 = 0;
       if (g_row < L_end) {
         const u64* st = reinterpret_cast<const u64*>(SH.state + t * TC_TILE_M + r);     // left there by this rollout's descent
         const u64 bp = st[0], bo = st[1];
         constexpr int VS = G::VS;
-        const u64 x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
-        const u64 x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
-        bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
+        x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
+        x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
       }
 #pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const uint32_t byte = (bits >> (8 * i)) & 0xFFu;
-        uint32_t w[4];
+      for (int j = 0; j < CPW; j++) {
+        const int cs = csb + j;
+        const uint32_t bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
 #pragma unroll
-        for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
-        const int c = 4 * cs + i;                                      // chunk of 8 operands in the row, 0..15
-        *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int i = 0; i < 4; i++) {
+          const uint32_t byte = (bits >> (8 * i)) & 0xFFu;
+          uint32_t w[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
+          const int c = 4 * cs + i;                                    // chunk of 8 operands in the row, 0..15
+          *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
       }
     }
     if (t >= ntiles) { wl += nlayers; __syncthreads(); continue; }      // idle tile: rejoin at the end-of-rollout barrier
     fence_proxy_async();
-    named_bar_sync(1 + t, 512);
+    named_bar_sync(1 + t, 32 * WPT);
 
     for (int l = 0; l < nlayers; l++, wl++) {
       const int s = wl % STAGES;
@@ -298,18 +304,20 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, SW ? 1 : FCfg<NT>::CTAS_PER
       if (SW && swapped && !is_head) {
         const bool keep = (l + 2 < nlayers);
         if constexpr (SW) {
-          if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, tmem_res, wq, cs, lane, l, keep, At);
-          else epilogue_swapped<FMT, 16>(tmem_acc, tmem_res, wq, cs, lane, l, keep, At);
+          if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At);
+          else epilogue_swapped<FMT, 16>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At);
         }
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
-        named_bar_sync(1 + t, 512);
+        named_bar_sync(1 + t, 32 * WPT);
       } else if (!is_head) {
         // epilogue: b = relu(acc) (base) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b)
         const bool keep = (l + 2 < nlayers);                            // the last trunk layer's residual is not read again
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
+        for (int ji = 0; ji < 2 * CPW; ji++) {
+          const int cs = csb + (ji >> 1), i = ji & 1;
+          const uint32_t lane_sel = lane_row + (uint32_t)(cs * 32);
           uint32_t va[16], vh[16];
           tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
           if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
@@ -334,12 +342,14 @@ __global__ void __launch_bounds__(FCfg<NT>::THREADS, SW ? 1 : FCfg<NT>::CTAS_PER
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
-        named_bar_sync(1 + t, 512);
+        named_bar_sync(1 + t, 32 * WPT);
       } else {
         // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> nn_out (global, read by the next search phase)
         float* o = P.nn_out + (size_t)g_row * Lay::OUTS;
 #pragma unroll
         for (int i = 0; i < 2; i++) {
+          const int cs = csb;                                           // NH <= 32: only a warp's first slice can hold head columns
+          const uint32_t lane_sel = lane_row + (uint32_t)(cs * 32);
           const int a0 = cs * 32 + i * 16;
           if (a0 < T.NH) {                                              // warp-uniform
             uint32_t v[16];
