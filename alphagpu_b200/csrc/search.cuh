@@ -667,11 +667,16 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     char* rec = gbase + (size_t)node * REC;
     // header, child ids and π̄ are the record's first bytes: every load of the level is issued before the flag is tested
     hw = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
-    uint32_t cw[AP / 4];
-#pragma unroll
-    for (int c = 0; c < AP / 8; c++) {
-      const uint2 cv = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8 * c);
-      cw[2 * c] = cv.x; cw[2 * c + 1] = cv.y;
+    // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
+    static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
+    u64 cw0, cw1 = 0;
+    {
+      const uint2 cv = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD);
+      cw0 = (u64)cv.x | ((u64)cv.y << 32);
+      if (AP == 16) {
+        const uint2 cv1 = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8);
+        cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
+      }
     }
     float pol[AP];
 #pragma unroll
@@ -680,11 +685,13 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
       pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
     }
     // the uniform of this depth does not depend on the loads above: Philox runs while they are in flight
+    const long long tP0 = (tr && depth == 0) ? clock64() : 0;
     if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
     const int w = depth & 3;
     const float u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
+    if (tr && depth == 0) { tr[11] += clock64() + (__float_as_int(u) & 0) - tP0; tr[12] += tP0 - tr0; }
     const int nchild = (int)((hw.x >> 16) & 0xFFu), flags = (int)(hw.x >> 24);
-    if (tr && depth == 0) trA = clock64() + (hw.x & 0) + (__float_as_int(pol[A - 1]) & 0) + (cw[0] & 0);
+    if (tr && depth == 0) trA = clock64() + (hw.x & 0) + (__float_as_int(pol[A - 1]) & 0) + ((u32)cw0 & 0);
     if (!(flags & F_EXPANDED)) {                                                      // while expanded[nindex]==1  (:110)
       // an existing node that is not expanded: the root before its first evaluation, or a terminal node
       SH.state[gl] = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
@@ -714,9 +721,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     pnode[depth] = (uint8_t)node;
     pmove[depth] = (uint8_t)best;
     if (depth < PATH_SMEM_DEPTH) { SH.pn[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)node; SH.pm[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)best; }
-    int c = 0;
-#pragma unroll
-    for (int k = 0; k < AP / 4; k++) if ((best >> 2) == k) c = (int)((cw[k] >> (8 * (best & 3))) & 0xFFu);
+    int c = (int)(((AP == 16 && best >= 8 ? cw1 : cw0) >> (8 * (best & 7))) & 0xFFu);
     if (c == 0) {                                                                     // allocate the child (:183-191)
       nn += 1;
       c = nn;
