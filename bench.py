@@ -128,6 +128,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    def stage(msg):                                                              # AGPU_BENCH_DEBUG=1: progress markers on stderr
+        if os.environ.get("AGPU_BENCH_DEBUG"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -146,6 +150,7 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"                                    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    stage("process group up")
     spec = ag.GameSpec.named("connect4")
     net = ag.ressimplesf(2 * spec.VectorizedState, spec.maxActions, WIDTH, BLOCKS, seed=0)
     ctx = ag.Context(spec, ROLLOUT, GAMES, WIDTH, BLOCKS, device=local_rank, nn_mode=args.nn_mode)
@@ -200,6 +205,42 @@ def main():
     ctx.profile(False)
     lay = ctx.layout()
     ctx.close()
+
+    stage("search legs done")
+    # ---- the training step that follows a generation (train.jl; SURVEY §8 f3): batch 8192 (main4IARow.jl:102-105) split over the ranks,
+    #      gradient all-reduce over NCCL when world > 1.  An extra, not part of the headline metric; never allowed to break the line. ----
+    train_info = None
+    try:
+        tnet = ag.ressimplesf_full(2 * spec.VectorizedState, spec.maxActions, spec.FeatureSize, WIDTH, BLOCKS, seed=0)
+        TB = 8192
+        trainer = ag.Trainer.for_network(tnet, TB // world, device=local_rank)
+        rng = np.random.default_rng(1)
+        st = (rng.random((TB, 2 * spec.VectorizedState)) < 0.3).astype(np.int8)
+        pol = rng.random((TB, spec.maxActions)).astype(np.float32); pol /= pol.sum(1, keepdims=True)
+        val = rng.choice(np.array([0, 0.5, 1], np.float32), size=TB)
+        fst = rng.integers(-1, 2, size=(TB, spec.FeatureSize)).astype(np.int8)
+        sl = ag.train.dp_slice(TB, rank, world)
+        tb = [a[sl] for a in (st, pol, val, fst)]
+        tstep = (lambda: trainer.step_dp(*tb)) if world > 1 else (lambda: trainer.step(*tb))
+        stage("trainer created")
+        for _ in range(3):
+            tstep()
+        stage("train warm-up done")
+        sync()
+        t0 = time.perf_counter()
+        tdev = []
+        for _ in range(20):
+            tstep()
+            tdev.append(sum(trainer.last_ms()))
+        sync()
+        twall = (time.perf_counter() - t0) / 20
+        train_info = {"net": "networkf 128x6 + feature head, fp32", "global_batch": TB, "ms_per_step_e2e": 1e3 * twall, "ms_per_step_device": float(np.median(tdev)),
+                              "samples_per_s": TB / twall, "allreduce": "nccl sum of one flat fp32 gradient" if world > 1 else None}
+        trainer.close()
+        stage("train leg done")
+    except Exception as e:                                                       # pragma: no cover
+        stage(f"train leg failed: {e!r}")
+        train_info = {"error": repr(e)}
 
     # ---- reduce over ranks: time = max, work = sum ----
     from alphagpu_b200 import parallel
@@ -261,37 +302,8 @@ def main():
         "roofline_nn": {"kernel": nn_name, "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
                         "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
+        "train_step": train_info,
     }
-
-    # ---- the training step that follows a generation (train.jl; SURVEY §8 f3): batch 8192 (main4IARow.jl:102-105) split over the ranks,
-    #      gradient all-reduce over NCCL when world > 1.  An extra, not part of the headline metric; never allowed to break the line. ----
-    try:
-        tnet = ag.ressimplesf_full(2 * spec.VectorizedState, spec.maxActions, spec.FeatureSize, WIDTH, BLOCKS, seed=0)
-        TB = 8192
-        trainer = ag.Trainer.for_network(tnet, TB // world, device=local_rank)
-        rng = np.random.default_rng(1)
-        st = (rng.random((TB, 2 * spec.VectorizedState)) < 0.3).astype(np.int8)
-        pol = rng.random((TB, spec.maxActions)).astype(np.float32); pol /= pol.sum(1, keepdims=True)
-        val = rng.choice(np.array([0, 0.5, 1], np.float32), size=TB)
-        fst = rng.integers(-1, 2, size=(TB, spec.FeatureSize)).astype(np.int8)
-        sl = ag.train.dp_slice(TB, rank, world)
-        tb = [a[sl] for a in (st, pol, val, fst)]
-        tstep = (lambda: trainer.step_dp(*tb)) if world > 1 else (lambda: trainer.step(*tb))
-        for _ in range(3):
-            tstep()
-        sync()
-        t0 = time.perf_counter()
-        tdev = []
-        for _ in range(20):
-            tstep()
-            tdev.append(sum(trainer.last_ms()))
-        sync()
-        twall = (time.perf_counter() - t0) / 20
-        line["train_step"] = {"net": "networkf 128x6 + feature head, fp32", "global_batch": TB, "ms_per_step_e2e": 1e3 * twall, "ms_per_step_device": float(np.median(tdev)),
-                              "samples_per_s": TB / twall, "allreduce": "nccl sum of one flat fp32 gradient" if world > 1 else None}
-        trainer.close()
-    except Exception as e:                                                       # pragma: no cover
-        line["train_step"] = {"error": repr(e)}
 
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (N=1 only) ----
     if world == 1 and not args.no_cpu_baseline:
