@@ -93,7 +93,7 @@ def run_reference(args, rank, world):
     spec = oracle.Spec(oracle.CONNECT4)
     p = ag.ressimplesf(2 * spec.VS, spec.A, WIDTH, BLOCKS, seed=0)
     net = oracle.Net(p.base, p.res, p.policy, p.policy_bias, p.value, p.value_bias)
-    sample_games = 256
+    sample_games = 1024                                                          # enough games to keep every host thread busy to the end
     times, sims = [], 0
     for i in range(args.warmup + args.steps):
         t = time.perf_counter()
