@@ -1,0 +1,12 @@
+"""Development: a few small self-play generations through every fused-kernel variant (for compute-sanitizer runs)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import alphagpu_b200 as ag
+for name, args, games, R in (("connect4", (), 700, 6), ("connect4", (), 40, 5), ("gobang", (3, 3), 300, 6)):
+    spec = ag.GameSpec.named(name, *args)
+    net = ag.ressimplesf(2 * spec.VectorizedState, spec.maxActions, 128, 5, seed=0)
+    ctx = ag.Context(spec, R, games, 128, 5)
+    ctx.set_weights(net)
+    res, st, _ = ctx.selfplay(R, games, cpuct=1.5, seed=3, want_samples=True)
+    print(name, games, list(map(int, res)), st["plies"], st["faults"], flush=True)
+    ctx.close()
