@@ -26,7 +26,7 @@ template <int NT, int WPT = 16> struct FCfg {
   static constexpr int THREADS = 32 * WPT * NT;                        // WPT warps per tile: 16 (one 32-column slice per warp) or 8 (two)
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 1024 + GAMES * (44 + 72);   // + alignment slack + barriers/bias/backup work list + rollout hand-off
+  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 2048 + GAMES * (44 + 72);   // + alignment slack + barriers/bias/backup work list + rollout hand-off
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
   static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
 };
@@ -128,6 +128,8 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   SH.leaf = reinterpret_cast<uint8_t*>(SH.hdr + C::GAMES);
   SH.pn = SH.leaf + C::GAMES;
   SH.pm = SH.pn + C::GAMES * PATH_SMEM_DEPTH;
+  constexpr int ITEM_MAP = 1024;                                       // backup items whose game is looked up in a byte map (the rest: binary search)
+  uint8_t* s_item = SH.pm + C::GAMES * PATH_SMEM_DEPTH;                // [ITEM_MAP] item -> local game
   // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
   // expand reads the outputs in between.  (Staying under 196 KB of shared memory keeps the next carve-out step — 32 KB of L1 — free.)
   SH.out = reinterpret_cast<float*>(sA);
@@ -196,32 +198,40 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
     const int last = (k == visits - 1);
     // ================= search phase =================
     if (k > 0) {
-      // (a) expand every game of the CTA (softmax, legal mask, prior), leaving value and path length in shared memory
-      if (has_game) s_eval[threadIdx.x] = expand_game1<G>(P, my_g, (int)threadIdx.x, SH, S.training, 0);   // one thread per game
-      __syncthreads();
-      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[0] += c - t_mark; t_mark = c; }
-      // (b) exclusive prefix sum of the path lengths (warp 0, GAMES/32 entries per lane)
-      if (warp == 0) {
+      // (a) expand every game of the CTA (softmax, legal mask, prior), one thread per game, leaving the leaf evaluation in shared memory;
+      // (b) meanwhile the last warp — never a game thread at these sizes — prefix-sums the path lengths of the previous descent and
+      //     fills the item -> game map of the backup phase
+      if (has_game) s_eval[threadIdx.x] = expand_game1<G>(P, my_g, (int)threadIdx.x, SH, S.training, 0);
+      if (warp == C::THREADS / 32 - 1) {
         constexpr int PER = C::GAMES / 32;
-        int loc[PER], sum = 0;
+        int loc[PER], dd[PER], sum = 0;
 #pragma unroll
-        for (int i = 0; i < PER; i++) { loc[i] = sum; sum += s_d[lane * PER + i]; }
+        for (int i = 0; i < PER; i++) { dd[i] = s_d[lane * PER + i]; loc[i] = sum; sum += dd[i]; }
         int incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
         const int excl = incl - sum;
 #pragma unroll
-        for (int i = 0; i < PER; i++) s_off[lane * PER + i] = excl + loc[i];
+        for (int i = 0; i < PER; i++) {
+          const int off = excl + loc[i];
+          s_off[lane * PER + i] = off;
+          for (int j = 0; j < dd[i]; j++) if (off + j < ITEM_MAP) s_item[off + j] = (uint8_t)(lane * PER + i);
+        }
         if (lane == 31) s_off[C::GAMES] = incl;
       }
       __syncthreads();
-      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[1] += c - t_mark; t_mark = c; }
+      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[0] += c - t_mark; t_mark = c; }
       // (c) backUp + re-solve of π̄: one (game, ancestor) item per THREAD, packed densely over the CTA — with a lane group per
       //     game only d of its 8 lanes (46 % on average) had an ancestor to work on, and the solve is 40 % of the search time
       const int items = s_off[C::GAMES];
       for (int i = threadIdx.x; i < items; i += C::THREADS) {
-        int lo = 0, hi = C::GAMES;                                     // largest gl with s_off[gl] <= i
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+        int lo = 0;
+        if (i < ITEM_MAP) {
+          lo = s_item[i];
+        } else {                                                       // largest gl with s_off[gl] <= i
+          int hi = C::GAMES;
+          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+        }
         backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
                        SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH);
       }
