@@ -137,7 +137,7 @@ struct EngineT : EngineBase {
   bool fused_swap = true;
   int fused_wpt = 8;               // warps per tile of the two-tile variant: 8 = 512 threads x 128 registers (16: 1024 x 64, 91 vs 84 ms)
   int fused_swap_max = 128;        // games per CTA up to which the 512-thread variant is launched
-  int num_sms = 148, fused_min_gpc = 32, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
+  int num_sms = 148, fused_min_gpc = 8, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };

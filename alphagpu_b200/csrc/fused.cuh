@@ -39,6 +39,12 @@ AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
       : "memory");
 }
 AG_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// one lane of a converged warp
+AG_D bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 AG_D void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -159,7 +165,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   auto load_layer = [&](int wl) {
     const int s = wl % STAGES, l = wl % nlayers;
     const uint32_t bytes = (l == nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
-    if (wl >= STAGES) mbar_wait(bar_empty + 8 * s, ((wl / STAGES) - 1) & 1);
+    if (NT == 2 && wl >= STAGES) mbar_wait(bar_empty + 8 * s, ((wl / STAGES) - 1) & 1);
     mbar_expect_tx(bar_full + 8 * s, bytes);
     bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + (size_t)l * TC_W_STAGE_BYTES, bytes, bar_full + 8 * s);
   };
@@ -182,7 +188,14 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
   const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
   const uint32_t lane_row = (uint32_t)(wq * 32) << 16;
-  const bool issuer = (warp % WPT) == 0 && lane == 0;
+  // The MMA-issuing warp of a tile takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived
+  // from values the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent
+  // `lane == 0` branch each MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int t_u = warp_u / WPT;
+  const bool issuer_warp = (warp_u % WPT) == 0;
+  const uint32_t tmem_acc_u = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(t_u * TC_N);
+  const uint32_t a_smem_u = smem_u32(sA) + (uint32_t)(t_u * TC_A_BYTES);
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
   // one thread per game for the descent and the expansion: its uid and node count stay in registers for the whole ply
@@ -193,6 +206,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   if (threadIdx.x < C::GAMES) s_d[threadIdx.x] = 0;
 
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
+  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of the issuer: weights wait, MMA issue, MMA done, epilogue, barrier
   long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): expand, scan, backup, select, network
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
@@ -277,39 +291,49 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
       const int s = wl % STAGES;
       const bool is_head = (l == nlayers - 1);
       const int nl = is_head ? T.NH : TC_N;
-      if (issuer) {
+      long long lt0 = 0, lt1 = 0, lt2 = 0;
+      const bool ltr = T.dbg != nullptr && threadIdx.x == 0 && !is_head;
+      if (ltr) lt0 = clock64();
+      if (issuer_warp) {
         mbar_wait(bar_full + 8 * s, (wl / STAGES) & 1);
-        if (wl == 0 && t == 1) mbar_wait(bar_stagger, 0);              // tile 1 trails tile 0 by one MMA phase
+        if (ltr) lt1 = clock64();
+        if (wl == 0 && t_u == 1) mbar_wait(bar_stagger, 0);            // tile 1 trails tile 0 by one MMA phase
         tc_fence_after();
-        const uint64_t ad0 = umma_desc(smem_u32(At));
-        const uint64_t bd0 = umma_desc(smem_u32(sW + s * TC_W_STAGE_BYTES));
-        const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
-        if (SW && swapped && !is_head) {
-          const uint32_t idesc = umma_idesc<FMT>(NS);                   // M = 128 out-features, N = NS games
+        if (elect_one()) {
+          const uint64_t ad0 = umma_desc(a_smem_u);
+          const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * TC_W_STAGE_BYTES));
+          const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
+          if (SW && swapped && !is_head) {
+            const uint32_t idesc = umma_idesc<FMT>(NS);                 // M = 128 out-features, N = NS games
 #pragma unroll
-          for (int ks = 0; ks < TC_N / 16; ks++) {
-            const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-            const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-            umma_bf16(tmem_acc, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
-          }
-        } else {
-          const uint32_t idesc = umma_idesc<FMT>(nl);
+            for (int ks = 0; ks < TC_N / 16; ks++) {
+              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+              umma_bf16(tmem_acc_u, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
+            }
+          } else {
+            const uint32_t idesc = umma_idesc<FMT>(nl);
 #pragma unroll
-          for (int ks = 0; ks < TC_N / 16; ks++) {
-            const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-            const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-            umma_bf16(tmem_acc, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+            for (int ks = 0; ks < TC_N / 16; ks++) {
+              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+              umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+            }
           }
+          umma_commit(bar_done + 8 * t_u);
+          if (NT == 2) umma_commit(bar_empty + 8 * s);                  // one tile: the requesting lane has itself seen the previous layer complete
+          if (wl == 0 && t_u == 0) umma_commit(bar_stagger);
         }
-        umma_commit(bar_done + 8 * t);
-        umma_commit(bar_empty + 8 * s);
-        if (wl == 0 && t == 0) umma_commit(bar_stagger);
+        __syncwarp();
+        if (ltr) lt2 = clock64();
       }
       // the weights two layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the issuer
       // the request sat on the critical path: 2 k cycles per rollout)
       if (warp == 1 && lane == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
       mbar_wait(bar_done + 8 * t, wl & 1);
       tc_fence_after();
+      long long lt3 = 0;
+      if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
 
       if (SW && swapped && !is_head) {
         const bool keep = (l + 2 < nlayers);
@@ -320,7 +344,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
+        long long lt4 = 0;
+        if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
         named_bar_sync(1 + t, 32 * WPT);
+        if (ltr) t_ly[4] += clock64() - lt4;
       } else if (!is_head) {
         // epilogue: b = relu(acc) (base) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b)
         const bool keep = (l + 2 < nlayers);                            // the last trunk layer's residual is not read again
@@ -352,7 +379,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
+        long long lt4 = 0;
+        if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
         named_bar_sync(1 + t, 32 * WPT);
+        if (ltr) t_ly[4] += clock64() - lt4;
       } else {
         // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> nn_out (global, read by the next search phase)
         float* o = P.nn_out + (size_t)g_row * Lay::OUTS;
@@ -393,6 +423,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   if (T.dbg && threadIdx.x == 0) {
     for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 32 + i] = t_ph[i];
     T.dbg[blockIdx.x * 32 + 5] = count; T.dbg[blockIdx.x * 32 + 6] = visits;
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 32 + 24 + i] = t_ly[i];
   }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)

@@ -22,6 +22,8 @@ for L in [int(x) for x in sys.argv[1:]] or [32768, 8192, 1024, 128]:
     ph = t[:, :5].mean(0) / 64
     print(f"L={L}: CTAs {len(t)} games/CTA {t[:,5].mean():.0f}  cycles per rollout: expand {ph[0]:.0f} scan {ph[1]:.0f} backup {ph[2]:.0f} select {ph[3]:.0f} "
           f"network {ph[4]:.0f}  total {ph.sum():.0f} ({ph.sum()/1.965e3:.1f} us)")
+    ly = t[:, 24:29].mean(0) / 64 / 6            # per trunk layer (6 per rollout for a 128x6 net)
+    print(f"      trunk layer (issuer thread): wait weights {ly[0]:.0f}, issue MMAs + commits {ly[1]:.0f}, wait done {ly[2]:.0f}, epilogue {ly[3]:.0f}, barrier {ly[4]:.0f}  = {ly.sum():.0f} cycles")
     x = t[:, 8:].sum(0).astype(float)
     if x[2] > 0:
         print(f"      thread 0: backup item load+update {x[0]/x[2]:.0f} cyc, solve {x[1]/x[2]:.0f} cyc ({x[2]/len(t)/64:.2f} items/rollout); "
