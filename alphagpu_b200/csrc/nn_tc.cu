@@ -94,6 +94,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
     const int g = seg_off + blockIdx.x * (TC_TILES * TC_TILE_M) + t * TC_TILE_M + r;
     unsigned char* At = sA + t * TC_A_BYTES;
     const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);                       // column offset of this tile
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0), t_u = warp_u / TC_WARPS_PER_TILE;   // the same values, visibly warp-uniform
+    const uint32_t tmem_acc_u = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(t_u * TC_N);
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(ch * 64);   // lane base of this warp's quarter, its column half
 
     // ---- A operand of the base layer: 0/1 encoding of the leaf position (decoder, mcts_gpu.jl:202-223) ----
@@ -158,31 +160,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
       const bool tracer = T.dbg && (warp % TC_WARPS_PER_TILE) == 0 && lane == 0;
       long long* tr = T.dbg ? T.dbg + (((size_t)blockIdx.x * TC_TILES + t) * 16 + l) * 4 : nullptr;
       if (tracer) tr[0] = clock64();
-      if ((warp % TC_WARPS_PER_TILE) == 0 && lane == 0) {
+      if ((warp_u % TC_WARPS_PER_TILE) == 0) {
         // ---- MMA issue: D[128 x nl] = A[128 x K] * W_l[nl x K]^T ----
+        // (warp-uniform branch, one elected lane issues: see elect_one in tc_ptx.cuh)
         mbar_wait(bar_full + 8 * s, (l / TC_STAGES) & 1);
         // stagger: tile 1 issues its first layer only after tile 0's first layer has drained, so that from then on one tile's
         // MMAs run while the other tile is in its epilogue (in lockstep both would share the tensor pipe, then both leave it idle)
         // (a one-shot barrier: its phase 0 completes once and never flips back, so a late tile 1 can not miss it)
-        if (l == 0 && t == 1) mbar_wait(bar_full + 8 * 8, 0);
+        if (l == 0 && t_u == 1) mbar_wait(bar_full + 8 * 8, 0);
         tc_fence_after();
-        // 8 K-steps of 16 (the base layer's operands are zero-padded to K = 128).  Fully unrolled with precomputed descriptor
-        // increments: a single thread issues these, and a rolled loop with per-step descriptor arithmetic measured ~180 cycles
-        // per MMA against the tensor pipe's 64 (profiles/r01_tc_trace.txt).
-        const uint64_t ad0 = umma_desc(smem_u32(At));
-        const uint64_t bd0 = umma_desc(smem_u32(sW + s * TC_W_STAGE_BYTES));
-        const uint32_t idesc = umma_idesc<FMT>(nl);
-        const uint64_t bstep = (uint64_t)((nl * 128) >> 4);              // second K tile of the weight image
+        if (elect_one()) {
+          // 8 K-steps of 16 (the base layer's operands are zero-padded to K = 128), fully unrolled with precomputed descriptor increments
+          const uint64_t ad0 = umma_desc(smem_u32(sA) + (uint32_t)(t_u * TC_A_BYTES));
+          const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * TC_W_STAGE_BYTES));
+          const uint32_t idesc = umma_idesc<FMT>(nl);
+          const uint64_t bstep = (uint64_t)((nl * 128) >> 4);            // second K tile of the weight image
 #pragma unroll
-        for (int ks = 0; ks < TC_N / 16; ks++) {
-          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-          umma_bf16(tmem_acc, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+          for (int ks = 0; ks < TC_N / 16; ks++) {
+            const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+            const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+            umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(bar_done + 8 * t_u);             // accumulator ready -> epilogue of this tile
+          umma_commit(bar_empty + 8 * s);              // weight stage consumed by this tile
+          if (l == 0 && t_u == 0) umma_commit(bar_full + 8 * 8);
+          if (t_u == 0 && l + 2 < T.nlayers) load_layer(l + 2);   // producer role: keep the ring two layers ahead
         }
-        umma_commit(bar_done + 8 * t);               // accumulator ready -> epilogue of this tile
-        umma_commit(bar_empty + 8 * s);              // weight stage consumed by this tile
-        if (l == 0 && t == 0) umma_commit(bar_full + 8 * 8);
-        if (t == 0 && l + 2 < T.nlayers) load_layer(l + 2);   // producer role: keep the ring two layers ahead
+        __syncwarp();
         if (tracer) tr[1] = clock64();
       }
       mbar_wait(bar_done + 8 * t, l & 1);

@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(W5_THREADS, 1) tc_mlp512_kernel(Tc512Args T, N
   float* sbias = reinterpret_cast<float*>(bars + 13);                  // [128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);               // the same value, visibly warp-uniform to the compiler
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 5), bar_done = smem_u32(bars + 10), bar_act = smem_u32(bars + 11);
 
   if (threadIdx.x == 0) {
@@ -108,11 +109,13 @@ __global__ void __launch_bounds__(W5_THREADS, 1) tc_mlp512_kernel(Tc512Args T, N
         }
       }
     }
-  } else if (warp == 16) {
+  } else if (warp_u == 16) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // the whole warp walks the schedule (uniform control flow, uniform operands); one elected lane issues
+    {
       int c = 0;
       const uint32_t a0 = smem_u32(sA);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
       for (int l = 0; l <= last_layer; l++) {
         mbar_wait(bar_act, l & 1);                                     // A operand of this layer is in shared memory
         tc_fence_after();
@@ -124,15 +127,19 @@ __global__ void __launch_bounds__(W5_THREADS, 1) tc_mlp512_kernel(Tc512Args T, N
             const int s = c % W5_STAGES;
             mbar_wait(bar_full + 8 * s, (c / W5_STAGES) & 1);
             tc_fence_after();
-            const uint64_t ad0 = umma_desc(a0 + kt * TC_KTILE_BYTES_A);
-            const uint64_t bd0 = umma_desc(smem_u32(sW + s * W5_CHUNK));
+            if (elect_one()) {
+              const uint64_t ad0 = umma_desc(a0 + kt * TC_KTILE_BYTES_A);
+              const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * W5_CHUNK));
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)
-              umma_bf16(tmem_base + (uint32_t)(nb * 128), ad0 + (uint64_t)((ks * 32) >> 4), bd0 + (uint64_t)((ks * 32) >> 4), idesc, (kt | ks) ? 1u : 0u);
-            umma_commit(bar_empty + 8 * s);                            // chunk consumed -> producer may refill the stage
+              for (int ks = 0; ks < 4; ks++)
+                umma_bf16(tmem_u + (uint32_t)(nb * 128), ad0 + (uint64_t)((ks * 32) >> 4), bd0 + (uint64_t)((ks * 32) >> 4), idesc, (kt | ks) ? 1u : 0u);
+              umma_commit(bar_empty + 8 * s);                          // chunk consumed -> producer may refill the stage
+            }
+            __syncwarp();
           }
         }
-        umma_commit(bar_done);                                         // the whole layer has drained
+        if (elect_one()) umma_commit(bar_done);                        // the whole layer has drained
+        __syncwarp();
       }
     }
   } else {
