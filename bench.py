@@ -90,6 +90,8 @@ def run_reference(args, rank, world):
     import oracle
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import alphagpu_b200 as ag
+    # every host thread the process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, and only rank 0 works here
+    oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     spec = oracle.Spec(oracle.CONNECT4)
     p = ag.ressimplesf(2 * spec.VS, spec.A, WIDTH, BLOCKS, seed=0)
     net = oracle.Net(p.base, p.res, p.policy, p.policy_bias, p.value, p.value_bias)
@@ -308,6 +310,7 @@ def main():
     # ---- CPU baseline: the oracle port on the host cores, bounded sample (N=1 only) ----
     if world == 1 and not args.no_cpu_baseline:
         import oracle
+        oracle.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
         ospec = oracle.Spec(oracle.CONNECT4)
         onet = oracle.Net(net.base, net.res, net.policy, net.policy_bias, net.value, net.value_bias)
         oracle.selfplay(ospec, onet, ROLLOUT, 32, cpuct=CPUCT, seed=0)           # warm the threads
