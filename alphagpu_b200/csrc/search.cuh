@@ -788,12 +788,27 @@ AG_D LeafEval expand_game1(const SearchParams& P, const int g, const int gl, con
     float e[A], ssum = 0.f;
 #pragma unroll
     for (int a = 0; a < A; a++) { e[a] = c_expf(fsub(x[a], m)); ssum = fadd(ssum, e[a]); }
+    // the two rounds of divisions (softmax, renormalisation over the legal moves) as packed fast-path batches when every operand is
+    // in the box of fdiv_fast (common.cuh), else the plain IEEE division: same quotients either way
+    {
+      float den[A], qn[A];
+      bool ok = fdiv_box_den(ssum);
+#pragma unroll
+      for (int a = 0; a < A; a++) { den[a] = ssum; ok = ok && fdiv_box_num(e[a]); }
+      if (ok) {
+        fdiv_fast_n<A>(e, den, qn);
+#pragma unroll
+        for (int a = 0; a < A; a++) e[a] = qn[a];
+      } else {
+#pragma unroll
+        for (int a = 0; a < A; a++) e[a] = fdiv(e[a], ssum);
+      }
+    }
     float normalize = 0.f;
     int acount = 0;
     bool legal[A];
 #pragma unroll
     for (int a = 0; a < A; a++) {
-      e[a] = fdiv(e[a], ssum);
       legal[a] = G::can_play(st, a + 1);
       normalize = fadd(normalize, legal[a] ? e[a] : 0.f);
       acount += legal[a] ? 1 : 0;
@@ -803,9 +818,21 @@ AG_D LeafEval expand_game1(const SearchParams& P, const int g, const int gl, con
     float pr[AP];
 #pragma unroll
     for (int a = 0; a < AP; a++) pr[a] = 0.f;
+    {
+      float num[A], den[A], qn[A];
+      bool ok = fdiv_box_den(normalize);
 #pragma unroll
-    for (int a = 0; a < A; a++)
-      if (legal[a]) pr[a] = rootmix ? fadd(fdiv(fmul(0.75f, e[a]), normalize), unif) : fdiv(e[a], normalize);
+      for (int a = 0; a < A; a++) { num[a] = rootmix ? fmul(0.75f, e[a]) : e[a]; den[a] = normalize; ok = ok && fdiv_box_num(num[a]); }
+      if (ok) {
+        fdiv_fast_n<A>(num, den, qn);
+      } else {
+#pragma unroll
+        for (int a = 0; a < A; a++) qn[a] = legal[a] ? fdiv(num[a], normalize) : 0.f;
+      }
+#pragma unroll
+      for (int a = 0; a < A; a++)
+        if (legal[a]) pr[a] = rootmix ? fadd(qn[a], unif) : qn[a];
+    }
 #pragma unroll
     for (int c = 0; c < AP / 4; c++) {
       const float4 pv = make_float4(pr[4 * c], pr[4 * c + 1], pr[4 * c + 2], pr[4 * c + 3]);
