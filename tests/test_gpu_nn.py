@@ -127,12 +127,14 @@ def test_tc_selfplay_properties_full_size():
 
 
 @pytest.mark.parametrize("name,games,R", [("connect4", 3000, 24), ("ttt", 1500, 16), ("connect4", 40000, 8),
-                                          ("connect4", 1, 1), ("connect4", 257, 2), ("connect4", 300, 255), ("ttt", 33, 200)])
+                                          ("connect4", 1, 1), ("connect4", 257, 2), ("connect4", 300, 255), ("ttt", 33, 200),
+                                          ("connect4", 148 * 64 + 1, 3), ("connect4", 148 * 128 + 9, 3)])
 def test_fused_ply_kernel_equals_separate_kernels(monkeypatch, name, games, R):
     """The persistent per-ply kernel (fused.cuh) and the per-rollout kernels (search.cuh + nn_tc.cu) run the same device functions
     and the same MMA sequence: a whole self-play generation must come out identical, bit for bit.  Game counts that are not
     multiples of 256 exercise partially filled tiles and CTAs; 40000 games exceed one CTA per SM (full 256-game CTAs); one game with
-    one rollout, and the maximum rollout count (node ids are bytes) with paths deeper than the 16 levels kept in shared memory."""
+    one rollout, and the maximum rollout count (node ids are bytes) with paths deeper than the 16 levels kept in shared memory; the last
+    two straddle the kernel-variant boundaries at 64 and 128 games per CTA (swapped / one tile / two tiles)."""
     pnet, _ = make_nets(GAME_SPECS[name], 128, 6, seed=11)
     outs = []
     for fused in ("1", "0"):
