@@ -9,3 +9,4 @@ from .game import GameSpec  # noqa: F401
 from .mcts_gpu import Context, PoolSample, duelnetwork, init, mcts, mcts_duel  # noqa: F401
 from .train import Trainer, traininPipe  # noqa: F401
 from .selfplay import elo_update, trainingPipeline  # noqa: F401
+from .fast_mcts import MctsContext, move_dictionaries, testvsordi  # noqa: F401

@@ -80,6 +80,69 @@ def test_alpha_solve_known_answer():
     assert d["action"][0, leaf[0] - 1] == 4
 
 
+def fmcts_policy_numpy(prior, w, n, c):
+    """The reference's OTHER statement of the same solve: FMCTS.newton + bestChild/extractRoot (fast_mcts.jl:41-69, 218-223, 293-302),
+    numpy float32, every action summed individually (no lumped prior_rem), q = w/n formed on the fly."""
+    A = len(prior)
+    visits = f32(1) + f32(np.sum(n))                                   # node.visits: own first visit + one per action visit
+    nact = int(np.sum(prior > 0))                                      # getActionNumber(state) = number of legal actions
+    lam = f32(f32(f32(c) * np.sqrt(visits, dtype=f32)) / f32(f32(nact) + visits))
+    alpha = f32(0)
+    for k in range(A):
+        gap = max(f32(lam * prior[k]), f32(1e-4))
+        alpha = max(alpha, gap if n[k] == 0 else f32(f32(w[k] / n[k]) + gap))
+    err = f32(np.inf)
+    for _ in range(100):
+        S, g = f32(0), f32(0)
+        for k in range(A):
+            top = f32(lam * prior[k])
+            bot = alpha if n[k] == 0 else f32(alpha - f32(w[k] / n[k]))
+            S = f32(S + f32(top / bot))
+            g = f32(g + f32(f32(-top) / f32(bot * bot)))
+        newerr = f32(S - f32(1))
+        if newerr < f32(0.001) or newerr == err:
+            break
+        alpha = f32(alpha - f32(newerr / g))
+        err = newerr
+    return alpha, [f32(top_k / (alpha if n[k] == 0 else f32(alpha - f32(w[k] / n[k]))))
+                   for k, top_k in enumerate(f32(lam) * prior.astype(f32))]
+
+
+def test_alpha_solve_agrees_with_the_references_cpu_statement():
+    """mcts_gpu.jl's kdescendTree! solve (oracle) and fast_mcts.jl's newton are two texts of one fixed point: same λ, same start, same
+    stopping rule, different summation grouping — α and π̄ agree to rounding on random node statistics (A = 7, 9, 49, 81; boards where
+    every action can be played from Position(), so that any subset can be given children)."""
+    rng = np.random.default_rng(17)
+    worst = 0.0
+    for A, name in ((7, "connect4"), (9, "ttt"), (49, "hex7"), (81, "gobang9")):
+        spec = oracle.Spec(*GAME_SPECS[name])
+        for trial in range(40):
+            prior = rng.uniform(0.01, 1, A).astype(f32)
+            prior[rng.uniform(size=A) < 0.2] = 0                        # illegal actions
+            if not np.any(prior > 0):
+                prior[0] = 1
+            prior = (prior / prior.sum(dtype=f32)).astype(f32)
+            legal = np.nonzero(prior > 0)[0]
+            order = [int(a) + 1 for a in rng.permutation(legal)[:rng.integers(0, len(legal) + 1)]]
+            visits = np.zeros(A, f32)
+            q = np.zeros(A, f32)
+            for a in order:
+                visits[a - 1] = f32(rng.integers(1, 30))
+                q[a - 1] = f32(rng.uniform(0, 1))
+            t = oracle.Tree(spec, A + 2, 1)
+            t.reinit(spec.position(1))
+            t.search_begin()
+            t.poke(0, 1, prior, q, visits, order)
+            t.select(0, 1.5, prob=np.full((1, 1, spec.maxLen), 0.5, f32))
+            pol = t.dump()["policy"][0, 0]
+            lam, alpha, iters, want = alpha_solve_numpy(prior, q, visits, order, 1.5)
+            assert np.array_equal(np.asarray(want, f32).view(np.uint32), pol.view(np.uint32))      # the oracle is the mcts_gpu text, bit for bit
+            alpha2, pol2 = fmcts_policy_numpy(prior, q * visits, visits, 1.5)
+            assert abs(float(alpha2) - float(alpha)) < 2e-5 * max(1.0, float(alpha))
+            worst = max(worst, float(np.max(np.abs(np.asarray(pol2, f32) - pol))))
+    assert worst < 1e-4, worst
+
+
 def rand_net(spec, n, k, seed):
     rng = np.random.default_rng(seed)
     glorot = lambda o, i: rng.uniform(-1, 1, size=(o, i)).astype(f32) * f32(np.sqrt(6.0 / (o + i)))
