@@ -95,7 +95,7 @@ def run_reference(args, rank, world):
     spec = oracle.Spec(oracle.CONNECT4)
     p = ag.ressimplesf(2 * spec.VS, spec.A, WIDTH, BLOCKS, seed=0)
     net = oracle.Net(p.base, p.res, p.policy, p.policy_bias, p.value, p.value_bias)
-    sample_games = 1024                                                          # enough games to keep every host thread busy to the end
+    sample_games = 4096                                                          # ~4 s per step on 16 cores: every host thread busy to the end
     times, sims = [], 0
     for i in range(args.warmup + args.steps):
         t = time.perf_counter()
@@ -314,7 +314,7 @@ def main():
         ospec = oracle.Spec(oracle.CONNECT4)
         onet = oracle.Net(net.base, net.res, net.policy, net.policy_bias, net.value, net.value_bias)
         oracle.selfplay(ospec, onet, ROLLOUT, 32, cpuct=CPUCT, seed=0)           # warm the threads
-        games = 1024
+        games = 8192                                                             # ~10 s of CPU work on the box's 16 cores
         t = time.perf_counter()
         _, ost = oracle.selfplay(ospec, onet, ROLLOUT, games, cpuct=CPUCT, seed=0)
         dt = time.perf_counter() - t
