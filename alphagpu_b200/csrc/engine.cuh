@@ -138,6 +138,9 @@ struct EngineT : EngineBase {
   int fused_wpt = 8;               // warps per tile of the two-tile variant: 8 = 512 threads x 128 registers (16: 1024 x 64, 91 vs 84 ms)
   int fused_swap_max = 128;        // games per CTA up to which the 512-thread variant is launched
   int num_sms = 148, fused_min_gpc = 8, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
+  // DUAL: above fused_dual_min games per SM the ply runs as one-tile CTAs of 256 threads x 128 registers, two per SM (fused.cuh: FCfg::DUAL)
+  bool fused_dual = false;
+  int fused_dual_min = 129, fused_dual_stagger_us = 0;
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -250,6 +253,21 @@ struct EngineT : EngineBase {
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
         if (const char* e = getenv("AGPU_FUSED_WPT")) fused_wpt = atoi(e) == 8 ? 8 : 16;
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1, 8>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1, 8>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (const char* e = getenv("AGPU_FUSED_DUAL")) fused_dual = atoi(e) != 0;
+        if (const char* e = getenv("AGPU_FUSED_DUAL_MIN")) fused_dual_min = atoi(e);
+        if (const char* e = getenv("AGPU_FUSED_DUAL_STAGGER_US")) fused_dual_stagger_us = atoi(e);
+        if (getenv("AGPU_DEBUG")) {                                     // development: resident CTAs per SM of the per-ply kernel variants
+          int occ_dual = 0, occ_two = 0, occ_sw = 0;
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dual, fused::ply_kernel<G, 1, 1, false, 8>, fused::FCfg<1, 8>::THREADS, fused::FCfg<1, 8>::SMEM);
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_two, fused::ply_kernel<G, 1, 2, false, 8>, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM);
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sw, fused::ply_kernel<G, 1, 1, true>, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM);
+          fprintf(stderr, "[agpu] ply_kernel CTAs per SM: dual %d (smem %d), two-tile %d (smem %d), small-batch %d (smem %d); dual=%d dual_min=%d\n",
+                  occ_dual, fused::FCfg<1, 8>::SMEM, occ_two, fused::FCfg<2, 8>::SMEM, occ_sw, fused::FCfg<1>::SMEM, (int)fused_dual, fused_dual_min);
+        }
         if (const char* e = getenv("AGPU_FUSED_SWAP")) fused_swap = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_SWAP_MAX")) fused_swap_max = atoi(e);
         use_fused = true;
@@ -279,10 +297,22 @@ struct EngineT : EngineBase {
       gpc = (gpc + 7) / 8 * 8;
       if (gpc < fused_min_gpc) gpc = fused_min_gpc;
       if (gpc > cap) gpc = cap;
+      // DUAL: enough games per SM to fill two one-tile CTAs -> spread them over 2 CTA slots per SM instead
+      const bool dual = fused_dual && fused_tiles == 2 && gpc >= fused_dual_min;
+      if (dual) {
+        S.pad = fused_dual_stagger_us;
+        gpc = (int)((L + 2 * num_sms - 1) / (2 * num_sms));
+        gpc = (gpc + 7) / 8 * 8;
+        if (gpc < fused_min_gpc) gpc = fused_min_gpc;
+        if (gpc > 128) gpc = 128;
+      }
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (gpc <= fused_swap_max && fused_swap) {
+        if (dual) {
+          if (fmt == 0) fused::ply_kernel<G, 0, 1, false, 8><<<grid, fused::FCfg<1, 8>::THREADS, fused::FCfg<1, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1, false, 8><<<grid, fused::FCfg<1, 8>::THREADS, fused::FCfg<1, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
+        } else if (gpc <= fused_swap_max && fused_swap) {
           // the tail of a generation: few games per CTA -> the 512-thread, 128-register, swapped-orientation variant
           if (fmt == 0) fused::ply_kernel<G, 0, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);

@@ -26,10 +26,19 @@ template <int NT, int WPT = 16> struct FCfg {
   static constexpr int THREADS = 32 * WPT * NT;                        // WPT warps per tile: 16 (one 32-column slice per warp) or 8 (two)
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + 2048 + GAMES * (44 + 72);   // + alignment slack + barriers/bias/backup work list + rollout hand-off
+  // DUAL (one tile, 8 warps): 256 threads x 128 registers and 112.5 KB of shared memory, so that TWO CTAs share an SM
+  // (2 x (112.5 + 1 reserved) KB = 227 of 228 KB, 2 x 256 TMEM columns, 2 x 256 x 128 registers): the two CTAs drift apart and one's
+  // search phase (latency chains, few issue slots) runs under the other's network phase.  The work area below is trimmed by 1 KB for it.
+  static constexpr bool DUAL = (NT == 1 && WPT == 8);
+  static constexpr int ITEM_MAP = 1024;                                // backup items whose game is looked up in a byte map
+  static constexpr int WORK = (DUAL ? 1024 : 2048) + GAMES * (44 + 72); // barriers/bias/backup work list + rollout hand-off
+  static constexpr int WORK_USED = 640 + GAMES * 32 + GAMES * 4 + (GAMES + 1) * 4 + 16 + GAMES * 68 + ITEM_MAP;   // as laid out in the kernel
+  static_assert(WORK_USED <= WORK, "shared-memory work area overflows its budget");
+  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK;   // + 1 KB alignment slack
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
   static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
 };
+static_assert(2 * (FCfg<1, 8>::SMEM + 1024) <= 228 * 1024, "two DUAL CTAs (plus 1 KB reserved each) must fit the SM's 228 KB");
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -86,7 +95,7 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs,
 // SW: the small-batch variant (host: games per CTA <= 128): one tile, 512 threads, one CTA per SM — 128 registers per thread instead
 // of 64 — and, up to 64 games, the trunk layers in the swapped orientation (below).
 template <class G, int FMT, int NT, bool SW = false, int WPT = 16>
-__global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 : FCfg<NT, WPT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+__global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 2 : (SW || WPT == 8) ? 1 : FCfg<NT, WPT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   static_assert(!SW || (NT == 1 && WPT == 16), "the swapped variant runs a single tile with 16 warps");
   static_assert(WPT == 16 || WPT == 8, "warps per tile");
   typedef Layout<G> Lay;
@@ -128,7 +137,8 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   SH.leaf = reinterpret_cast<uint8_t*>(SH.hdr + C::GAMES);
   SH.pn = SH.leaf + C::GAMES;
   SH.pm = SH.pn + C::GAMES * PATH_SMEM_DEPTH;
-  constexpr int ITEM_MAP = 1024;                                       // backup items whose game is looked up in a byte map (the rest: binary search)
+  constexpr int ITEM_MAP = C::ITEM_MAP;                                // backup items whose game is looked up in a byte map (the rest: binary search)
+  static_assert(sizeof(LeafEval) == 32 && sizeof(NodeHdr) == 8, "FCfg::WORK_USED assumes these sizes");
   uint8_t* s_item = SH.pm + C::GAMES * PATH_SMEM_DEPTH;                // [ITEM_MAP] item -> local game
   // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
   // expand reads the outputs in between.  (Staying under 196 KB of shared memory keeps the next carve-out step — 32 KB of L1 — free.)
@@ -198,6 +208,13 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
   if (threadIdx.x < C::GAMES) s_d[threadIdx.x] = 0;
+
+  // DUAL, optional (S.pad = microseconds): the second half of the grid — the CTAs that land as second residents of their SMs — starts
+  // late by about half a rollout, so that the two residents begin in opposite phases instead of finding them by contention
+  if (C::DUAL && S.pad > 0 && (int)blockIdx.x >= ((int)gridDim.x + 1) / 2) {
+    const long long until = clock64() + (long long)S.pad * 1965;
+    while (clock64() < until) __nanosleep(1000);
+  }
 
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
   long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of the issuer: weights wait, MMA issue, MMA done, epilogue, barrier
