@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 cd "${GRAFT_REPO_ROOT:-.}"
 echo "start $(date +%s)" > gpurun_out/r01b_timeline.txt
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/r01b_gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r01b_gpu_tests.log
+timeout 400 python -m pytest tests -m gpu -q > gpurun_out/r01b_gpu_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r01b_gpu_tests.log
 echo "pytest done $(date +%s)" >> gpurun_out/r01b_timeline.txt
 AGPU_DEBUG=1 timeout 240 python scripts/dual_experiment.py > gpurun_out/r01b_dual_experiment.txt 2> gpurun_out/r01b_dual_experiment.err; echo "rc=$?" >> gpurun_out/r01b_dual_experiment.txt
 echo "dual done $(date +%s)" >> gpurun_out/r01b_timeline.txt
