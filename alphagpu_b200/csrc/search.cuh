@@ -107,6 +107,29 @@ struct SearchParams {
 // thousand cycles each on the serial chain descent -> encode -> network -> expand -> backup -> descent.  Global memory keeps a copy
 // of everything (the stores are off the critical path), so the stand-alone kernels and the read-back entry points see the same data.
 constexpr int PATH_SMEM_DEPTH = 16;          // path entries per game held in shared memory; deeper levels are read from global
+
+// Loads of the records ON A PATH (descent and backup).  Development variant -DAG_L2_HINT=1: they carry an L2 evict_last policy, so that
+// the lines of nodes which are visited again and again outlive those of leaves that never are (the live trees, 400 MB at the end of a
+// 32768-game ply, do not fit the 126 MB L2).  Default build: plain loads.
+#ifndef AG_L2_HINT
+#define AG_L2_HINT 0
+#endif
+#if AG_L2_HINT
+AG_D u64 l2_hot_policy() { u64 p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+AG_D uint2 hot_ld_u2(const void* a) {
+  uint2 v; asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_hot_policy()) : "memory"); return v;
+}
+AG_D uint4 hot_ld_u4(const void* a) {
+  uint4 v; asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(l2_hot_policy()) : "memory"); return v;
+}
+AG_D float4 hot_ld_f4(const void* a) {
+  float4 v; asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(l2_hot_policy()) : "memory"); return v;
+}
+#else
+AG_D uint2 hot_ld_u2(const void* a) { return *reinterpret_cast<const uint2*>(a); }
+AG_D uint4 hot_ld_u4(const void* a) { return *reinterpret_cast<const uint4*>(a); }
+AG_D float4 hot_ld_f4(const void* a) { return *reinterpret_cast<const float4*>(a); }
+#endif
 template <class G>
 struct RolloutShared {
   typename G::State* state;  // [GAMES] state of the leaf
@@ -587,22 +610,22 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
         int vis[AP], ch[AP], ord[AP];
 #pragma unroll
         for (int c = 0; c < AP / 4; c++) {
-          const float4 pv = *reinterpret_cast<const float4*>(nrec + Lay::OFF_PRIOR + 16 * c);
-          const float4 qv = *reinterpret_cast<const float4*>(nrec + Lay::OFF_Q + 16 * c);
+          const float4 pv = hot_ld_f4(nrec + Lay::OFF_PRIOR + 16 * c);
+          const float4 qv = hot_ld_f4(nrec + Lay::OFF_Q + 16 * c);
           p[4 * c] = pv.x; p[4 * c + 1] = pv.y; p[4 * c + 2] = pv.z; p[4 * c + 3] = pv.w;
           q[4 * c] = qv.x; q[4 * c + 1] = qv.y; q[4 * c + 2] = qv.z; q[4 * c + 3] = qv.w;
         }
 #pragma unroll
         for (int c = 0; c < AP / 8; c++) {
-          const uint4 vv = *reinterpret_cast<const uint4*>(nrec + Lay::OFF_VIS + 16 * c);
+          const uint4 vv = hot_ld_u4(nrec + Lay::OFF_VIS + 16 * c);
           const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
 #pragma unroll
           for (int e = 0; e < 4; e++) { vis[8 * c + 2 * e] = (int)(w4[e] & 0xFFFFu); vis[8 * c + 2 * e + 1] = (int)(w4[e] >> 16); }
         }
 #pragma unroll
         for (int c = 0; c < AP / 8; c++) {          // child bytes then order bytes, AP bytes each, contiguous
-          const uint2 cv = *reinterpret_cast<const uint2*>(nrec + Lay::OFF_CHILD + 8 * c);
-          const uint2 ov = *reinterpret_cast<const uint2*>(nrec + Lay::OFF_ORDER + 8 * c);
+          const uint2 cv = hot_ld_u2(nrec + Lay::OFF_CHILD + 8 * c);
+          const uint2 ov = hot_ld_u2(nrec + Lay::OFF_ORDER + 8 * c);
           const uint32_t cw[2] = {cv.x, cv.y}, ow[2] = {ov.x, ov.y};
 #pragma unroll
           for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
@@ -666,22 +689,22 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   while (true) {
     char* rec = gbase + (size_t)node * REC;
     // header, child ids and π̄ are the record's first bytes: every load of the level is issued before the flag is tested
-    hw = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
+    hw = hot_ld_u2(rec + Lay::OFF_HDR);
     // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
     static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
     u64 cw0, cw1 = 0;
     {
-      const uint2 cv = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD);
+      const uint2 cv = hot_ld_u2(rec + Lay::OFF_CHILD);
       cw0 = (u64)cv.x | ((u64)cv.y << 32);
       if (AP == 16) {
-        const uint2 cv1 = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8);
+        const uint2 cv1 = hot_ld_u2(rec + Lay::OFF_CHILD + 8);
         cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
       }
     }
     float pol[AP];
 #pragma unroll
     for (int c = 0; c < AP / 4; c++) {
-      const float4 pv = *reinterpret_cast<const float4*>(rec + Lay::OFF_POLICY + 16 * c);
+      const float4 pv = hot_ld_f4(rec + Lay::OFF_POLICY + 16 * c);
       pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
     }
     // the uniform of this depth does not depend on the loads above: Philox runs while they are in flight
