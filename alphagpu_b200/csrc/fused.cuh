@@ -144,6 +144,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
   // expand reads the outputs in between.  (Staying under 196 KB of shared memory keeps the next carve-out step — 32 KB of L1 — free.)
   SH.out = reinterpret_cast<float*>(sA);
   SH.out_tile_stride = TC_A_BYTES / 4;
+  // ... and so does the root's descent view (search.cuh: RootSlot), in the second half of the same idle buffer
+  SH.root = AG_ROOT_SMEM ? sA + TC_A_BYTES / 2 : nullptr;
+  SH.root_tile_stride = TC_A_BYTES;
+  static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_A_BYTES / 2 && TC_TILE_M * RootSlot<Lay::APAD>::BYTES <= TC_A_BYTES / 2, "outputs and root slots share the idle A tile");
   static_assert(sizeof(typename G::State) + 8 + 1 + 2 * PATH_SMEM_DEPTH <= 68, "rollout hand-off budget per game");
   static_assert(FCfg<2>::SMEM <= 195 * 1024, "shared memory beyond the 196 KB carve-out costs 32 KB of L1");
 
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
           while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
         }
         backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
-                       SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH);
+                       SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH,
+                       AG_ROOT_SMEM ? SH.root + (lo >> 7) * SH.root_tile_stride + (lo & 127) * RootSlot<Lay::APAD>::BYTES : nullptr);
       }
       __syncthreads();
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }

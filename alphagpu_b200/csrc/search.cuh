@@ -140,6 +140,21 @@ struct RolloutShared {
   uint8_t* leaf;             // [GAMES]
   uint8_t* pn;               // [GAMES][PATH_SMEM_DEPTH] path nodes
   uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
+  unsigned char* root;       // AG_ROOT_SMEM: descent fields of the ROOT record (header, child ids, π̄), RootSlot<AP>::BYTES per game, left by the
+  int root_tile_stride;      //   backup item that re-solved the root; row gl at root + (gl / 128) * root_tile_stride + (gl % 128) * BYTES
+};
+
+// The root is on every path: each rollout's backup rewrites its π̄ and the next descent reads it back first thing — through L2, because the
+// writer is another thread (2 k cycles at 223 games per CTA, 0.6 k at 8).  The backup item of the root therefore also leaves the
+// descent's view of the record in shared memory.  Valid from the third rollout on: rollout 0 finds the root unexpanded (path length 0),
+// rollout 1 descends through it, so from rollout 2 on every backup phase has a root item.
+#ifndef AG_ROOT_SMEM
+#define AG_ROOT_SMEM 0
+#endif
+template <int AP> struct RootSlot {
+  static constexpr int OFF_CHILD = 8;                                  // after the 8-byte header
+  static constexpr int OFF_POLICY = (8 + AP + 15) & ~15;
+  static constexpr int BYTES = OFF_POLICY + 4 * AP;                    // 48 (AP = 8), 96 (AP = 16)
 };
 
 // One independent slice of the live games.  The rollout loop of a slice is replayed from a CUDA graph on its own stream, so
@@ -589,7 +604,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
 template <class G>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
-                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr) {
+                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr, unsigned char* s_root = nullptr) {
   const long long tr0 = tr ? clock64() : 0;
   typedef Layout<G> Lay;
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
@@ -630,7 +645,12 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
         }
+#if AG_ROOT_SMEM
+        const uint2 hdr_w = hot_ld_u2(nrec + Lay::OFF_HDR);
+        const int nchild = (int)((hdr_w.x >> 16) & 0xFFu);
+#else
         const int nchild = reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR)->nchild;
+#endif
         // running mean of the child's value from this node's point of view (:319-320)
         float qold = 0.f; int vold = 0;
 #pragma unroll
@@ -658,6 +678,21 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
             *reinterpret_cast<float4*>(nrec + Lay::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
+#if AG_ROOT_SMEM
+          if (s_root != nullptr && jj == 0) {                                        // the root: the next descent starts from this copy
+            *reinterpret_cast<uint2*>(s_root) = hdr_w;
+#pragma unroll
+            for (int c = 0; c < AP / 8; c++) {
+              uint32_t lo = 0, hi = 0;
+#pragma unroll
+              for (int e = 0; e < 4; e++) { lo |= (uint32_t)ch[8 * c + e] << (8 * e); hi |= (uint32_t)ch[8 * c + 4 + e] << (8 * e); }
+              *reinterpret_cast<uint2*>(s_root + RootSlot<AP>::OFF_CHILD + 8 * c) = make_uint2(lo, hi);
+            }
+#pragma unroll
+            for (int c = 0; c < AP / 4; c++)
+              *reinterpret_cast<float4*>(s_root + RootSlot<AP>::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
+          }
+#endif
         }
       }
     }
@@ -689,23 +724,41 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   while (true) {
     char* rec = gbase + (size_t)node * REC;
     // header, child ids and π̄ are the record's first bytes: every load of the level is issued before the flag is tested
-    hw = hot_ld_u2(rec + Lay::OFF_HDR);
-    // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
     static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
     u64 cw0, cw1 = 0;
+    float pol[AP];
+#if AG_ROOT_SMEM
+    if (depth == 0 && rollout >= 2 && SH.root != nullptr) {
+      // the root as the backup phase of this rollout left it in shared memory (RootSlot)
+      const unsigned char* sl = SH.root + (gl >> 7) * SH.root_tile_stride + (gl & 127) * RootSlot<AP>::BYTES;
+      hw = *reinterpret_cast<const uint2*>(sl);
+      const uint2 cv = *reinterpret_cast<const uint2*>(sl + RootSlot<AP>::OFF_CHILD);
+      cw0 = (u64)cv.x | ((u64)cv.y << 32);
+      if (AP == 16) {
+        const uint2 cv1 = *reinterpret_cast<const uint2*>(sl + RootSlot<AP>::OFF_CHILD + 8);
+        cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
+      }
+#pragma unroll
+      for (int c = 0; c < AP / 4; c++) {
+        const float4 pv = *reinterpret_cast<const float4*>(sl + RootSlot<AP>::OFF_POLICY + 16 * c);
+        pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
+      }
+    } else
+#endif
     {
+      hw = hot_ld_u2(rec + Lay::OFF_HDR);
+      // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
       const uint2 cv = hot_ld_u2(rec + Lay::OFF_CHILD);
       cw0 = (u64)cv.x | ((u64)cv.y << 32);
       if (AP == 16) {
         const uint2 cv1 = hot_ld_u2(rec + Lay::OFF_CHILD + 8);
         cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
       }
-    }
-    float pol[AP];
 #pragma unroll
-    for (int c = 0; c < AP / 4; c++) {
-      const float4 pv = hot_ld_f4(rec + Lay::OFF_POLICY + 16 * c);
-      pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
+      for (int c = 0; c < AP / 4; c++) {
+        const float4 pv = hot_ld_f4(rec + Lay::OFF_POLICY + 16 * c);
+        pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
+      }
     }
     // the uniform of this depth does not depend on the loads above: Philox runs while they are in flight
     const long long tP0 = (tr && depth == 0) ? clock64() : 0;
