@@ -25,6 +25,17 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# stdout carries exactly ONE JSON line: everything else that lands on file descriptor 1 (NCCL prints its version banner there at
+# NCCL_DEBUG=VERSION/WARN/INFO, torchrun children inherit it) is sent to stderr, and the line is written to the saved descriptor.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 GAMES, ROLLOUT, WIDTH, BLOCKS, CPUCT = 32768, 64, 128, 6, 1.5
 WORKLOAD = "connect4_densenet128x6_rollout64_games32768"
 METRIC = "selfplay_mcts_sims_per_sec"
@@ -113,7 +124,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": v, "unit": "sims/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} x {sample_games} Connect4 games, 128x6 fp32 net, 64 rollouts, to completion ({sims} sims)"},
             "e2e": {"value": v, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -148,8 +159,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"                                    # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     stage("process group up")
@@ -322,7 +331,7 @@ def main():
                                 "sample": f"{games} of {GAMES} Connect4 games played to the end, same net in fp32, {ost['sims']} sims in {dt:.1f} s"}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

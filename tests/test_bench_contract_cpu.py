@@ -34,6 +34,10 @@ def test_committed_bench_lines_follow_the_contract():
     _check_line(d2, 2)
     d1 = json.load(open(os.path.join(ROOT, "profiles", "r01_bench_fused.json")))
     assert d2["value"] > 1.8 * d1["value"] * 0.9          # weak scaling: two GPUs play twice the games in about the same time
+    # the lines of the last session of round 1 (1, 2 and 4 GPUs of one box, same commit)
+    e1, e2, e4 = (json.load(open(os.path.join(ROOT, "profiles", f"r01e_bench{s}.json"))) for s in ("", "_2gpu", "_4gpu"))
+    _check_line(e1, 1); _check_line(e2, 2); _check_line(e4, 4)
+    assert e2["value"] > 1.9 * e1["value"] and e4["value"] > 3.8 * e1["value"]
 
 
 def test_reference_arm_runs_here_and_uses_the_host_threads():
@@ -41,6 +45,7 @@ def test_reference_arm_runs_here_and_uses_the_host_threads():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
+    assert len(out.stdout.strip().splitlines()) == 1          # stdout is the one JSON line (library banners on fd 1 are sent to stderr)
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "sims/s" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
