@@ -246,3 +246,61 @@ def test_fdiv_fast_matches_ieee_division():
     mism, flagged = int(out[0]), int(out[1])
     assert mism == 0
     assert 0.05 * (1 << 30) < flagged < 0.4 * (1 << 30)      # the out-of-box band is exercised, the box is not empty
+
+
+def _golden(name):
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)) as f:
+        return json.load(f)
+
+
+def test_selfplay_matches_the_committed_digests():
+    """The CUDA path against a COMMITTED fixture (tests/golden/selfplay_digests.json, frozen oracle outputs): whole self-play generations
+    with the fp32 evaluator hash to the stored SHA-256 — every state, policy, player, value, fstate, game id and ply of every sample."""
+    import os
+    import sys
+    import alphagpu_b200 as ag
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_selfplay_digests import digest
+    for c in _golden("selfplay_digests.json"):
+        name, games, R, n, k, net_seed, seed, uid_base, cpuct = c["case"]
+        pnet, _ = make_nets(GAME_SPECS[name], n, k, seed=net_seed)
+        ctx = ctx_for(name, R, games, n, k)
+        ctx.set_weights(pnet)
+        res, stats, smp = ctx.selfplay(R, games, cpuct=cpuct, seed=seed, uid_base=uid_base)
+        ctx.close()
+        assert [int(x) for x in res] == c["results"] and len(smp["player"]) == c["samples"], name
+        assert digest(smp, res) == c["digest"], name
+
+
+def test_plugin_surface_against_golden_traces():
+    """tests/golden/kat_games.json replayed through the C ABI (Position / canPlay / play / isOver on the device): bitboards, side to move,
+    round counter, legality and outcome after every move equal the committed vectors."""
+    import alphagpu_b200 as ag
+    ctxs = {}
+    for case in _golden("kat_games.json"):
+        key = tuple(case["spec"])
+        if key not in ctxs:
+            ctxs[key] = ag.Context(ag.GameSpec(*key), 4, 8, 128, 2, 0, 1)
+        ctx = ctxs[key]
+        pos = ctx.Position(1)
+        for step in case["trace"]:
+            if step["move"] is not None:
+                assert ctx.canPlay(pos)[0, step["move"] - 1], case["name"]
+                pos = ctx.play(pos, step["move"])
+            p = pos[0]
+            assert [hex(int(x)) for x in p["bplayer"]["chunks"]] == step["bplayer"], case["name"]
+            assert [hex(int(x)) for x in p["bopponent"]["chunks"]] == step["bopponent"], case["name"]
+            if step["legalplay"] is not None:
+                assert [hex(int(x)) for x in p["legalplay"]["chunks"]] == step["legalplay"], case["name"]
+            assert int(p["player"]) == step["player"]
+            if pos.dtype.itemsize == 104:
+                assert int(p["aux"]) == step["aux"]
+            over, res = ctx.isOver(pos)
+            assert bool(over[0]) == step["over"]
+            if step["over"]:
+                assert int(res[0]) == step["result"]
+            assert [int(a) + 1 for a in np.nonzero(ctx.canPlay(pos)[0])[0]] == step["legal"], case["name"]
+    for ctx in ctxs.values():
+        ctx.close()

@@ -250,3 +250,22 @@ def test_selfplay_and_duel_complete():
     assert np.array_equal(ra + rb, res)
     dres, dst = oracle.duel(spec, net, rand_net(spec, 32, 2, 2), 8, 32, seed=5)
     assert dres.sum() == 32
+
+
+def test_selfplay_digests_match_the_committed_fixture():
+    """tests/golden/selfplay_digests.json (made by tests/golden/make_selfplay_digests.py): whole oracle self-play generations, frozen as
+    SHA-256 over every sample array.  Any change to the oracle that moves a single bit of a single sample shows up here; the GPU twin of
+    this test (tests/test_gpu_parity.py) holds the CUDA path to the same fixture."""
+    import json
+    import os
+    import sys
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    sys.path.insert(0, golden)
+    import make_selfplay_digests as m
+    with open(os.path.join(golden, "selfplay_digests.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 5
+    for c in cases:
+        got = m.oracle_case(tuple(c["case"]))
+        assert got["results"] == c["results"] and got["samples"] == c["samples"], c["case"]
+        assert got["digest"] == c["digest"], c["case"]
