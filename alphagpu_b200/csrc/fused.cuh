@@ -34,7 +34,9 @@ template <int NT, int WPT = 16> struct FCfg {
   static constexpr int WORK = (DUAL ? 1024 : 2048) + GAMES * (44 + 72); // barriers/bias/backup work list + rollout hand-off
   static constexpr int WORK_USED = 640 + GAMES * 32 + GAMES * 4 + (GAMES + 1) * 4 + 16 + GAMES * 68 + ITEM_MAP;   // as laid out in the kernel
   static_assert(WORK_USED <= WORK, "shared-memory work area overflows its budget");
-  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK;   // + 1 KB alignment slack
+  // AG_TREE_SMEM (KB): node cache of the one-tile, 16-warp kernels (the small-batch variant of the tail), after the work area
+  static constexpr int TREE_BYTES = (NT == 1 && WPT == 16) ? AG_TREE_SMEM * 1024 : 0;
+  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
   static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
 };
@@ -147,6 +149,9 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
   // ... and so does the root's descent view (search.cuh: RootSlot), in the second half of the same idle buffer
   SH.root = AG_ROOT_SMEM ? sA + TC_A_BYTES / 2 : nullptr;
   SH.root_tile_stride = TC_A_BYTES;
+  // node cache (AG_TREE_SMEM): the first nc_nodes nodes of each of this CTA's games; the fewer games, the deeper the cache
+  SH.nc_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sW + STAGES * TC_W_STAGE_BYTES + C::WORK) + 15) & ~uintptr_t(15));
+  SH.nc_nodes = C::TREE_BYTES > 0 ? min(P.R, (C::TREE_BYTES - 16) / (RootSlot<Lay::APAD>::BYTES * count)) : 0;
   static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_A_BYTES / 2 && TC_TILE_M * RootSlot<Lay::APAD>::BYTES <= TC_A_BYTES / 2, "outputs and root slots share the idle A tile");
   static_assert(sizeof(typename G::State) + 8 + 1 + 2 * PATH_SMEM_DEPTH <= 68, "rollout hand-off budget per game");
   static_assert(FCfg<2>::SMEM <= 195 * 1024, "shared memory beyond the 196 KB carve-out costs 32 KB of L1");
@@ -212,6 +217,19 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
   if (threadIdx.x < C::GAMES) s_d[threadIdx.x] = 0;
+#if AG_TREE_SMEM
+  // fill the node cache with the nodes that exist when the ply starts (the root alone after root_reset); read back only by this thread
+  if (has_game) {
+    const char* gb = P.tree + (size_t)my_g * P.game_stride;
+    for (int nd = 0; nd < min(my_nn, SH.nc_nodes); nd++) {
+      unsigned char* sl = node_cache_slot<G>(SH, (int)threadIdx.x, nd);
+      const char* rec = gb + (size_t)nd * Lay::REC;
+      *reinterpret_cast<uint2*>(sl) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
+      for (int c = 0; c < Lay::APAD / 8; c++) *reinterpret_cast<uint2*>(sl + RootSlot<Lay::APAD>::OFF_CHILD + 8 * c) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8 * c);
+      for (int c = 0; c < Lay::APAD / 4; c++) *reinterpret_cast<float4*>(sl + RootSlot<Lay::APAD>::OFF_POLICY + 16 * c) = *reinterpret_cast<const float4*>(rec + Lay::OFF_POLICY + 16 * c);
+    }
+  }
+#endif
 
   // DUAL, optional (S.pad = microseconds): the second half of the grid — the CTAs that land as second residents of their SMs — starts
   // late by about half a rollout, so that the two residents begin in opposite phases instead of finding them by contention
@@ -263,7 +281,8 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
         }
         backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
                        SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH,
-                       AG_ROOT_SMEM ? SH.root + (lo >> 7) * SH.root_tile_stride + (lo & 127) * RootSlot<Lay::APAD>::BYTES : nullptr);
+                       AG_ROOT_SMEM ? SH.root + (lo >> 7) * SH.root_tile_stride + (lo & 127) * RootSlot<Lay::APAD>::BYTES : nullptr,
+                       SH.nc_nodes > 0 ? SH.nc_base + (size_t)lo * SH.nc_nodes * RootSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
       }
       __syncthreads();
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }

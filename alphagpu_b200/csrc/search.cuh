@@ -142,6 +142,8 @@ struct RolloutShared {
   uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
   unsigned char* root;       // AG_ROOT_SMEM: descent fields of the ROOT record (header, child ids, π̄), RootSlot<AP>::BYTES per game, left by the
   int root_tile_stride;      //   backup item that re-solved the root; row gl at root + (gl / 128) * root_tile_stride + (gl % 128) * BYTES
+  unsigned char* nc_base;    // AG_TREE_SMEM: write-through copy of the descent fields of the first nc_nodes nodes of every game of the CTA,
+  int nc_nodes;              //   entry (gl, node) at nc_base + (gl * nc_nodes + node) * RootSlot<AP>::BYTES; 0 = no cache
 };
 
 // The root is on every path: each rollout's backup rewrites its π̄ and the next descent reads it back first thing — through L2, because the
@@ -151,11 +153,32 @@ struct RolloutShared {
 #ifndef AG_ROOT_SMEM
 #define AG_ROOT_SMEM 0
 #endif
+// -DAG_TREE_SMEM=<KB> (development variant, NOT YET RUN ON A GPU): the small-batch per-ply kernel spends <KB> of shared memory on a
+// write-through cache of the descent fields (header, child ids, π̄ — the RootSlot layout) of the first nodes of each of its games.  In
+// the tail of a generation a CTA holds <= 32 games and a rollout is a latency chain; a level of the descent is then a shared-memory read
+// instead of an L2 round trip.  Every writer of those fields (node allocation in the descent, expand, the π̄ re-solve of the backup)
+// updates global memory as before AND the cache entry; global memory stays authoritative for everything else.
+#ifndef AG_TREE_SMEM
+#define AG_TREE_SMEM 0
+#endif
+#if AG_TREE_SMEM && AG_ROOT_SMEM
+#error "AG_TREE_SMEM subsumes AG_ROOT_SMEM: enable one of them"
+#endif
 template <int AP> struct RootSlot {
   static constexpr int OFF_CHILD = 8;                                  // after the 8-byte header
   static constexpr int OFF_POLICY = (8 + AP + 15) & ~15;
   static constexpr int BYTES = OFF_POLICY + 4 * AP;                    // 48 (AP = 8), 96 (AP = 16)
 };
+// cache entry of (local game gl, node) or nullptr
+template <class G>
+AG_D unsigned char* node_cache_slot(const RolloutShared<G>& SH, const int gl, const int node) {
+#if AG_TREE_SMEM
+  return node < SH.nc_nodes ? SH.nc_base + (size_t)(gl * SH.nc_nodes + node) * RootSlot<Layout<G>::APAD>::BYTES : nullptr;
+#else
+  (void)SH; (void)gl; (void)node;
+  return nullptr;
+#endif
+}
 
 // One independent slice of the live games.  The rollout loop of a slice is replayed from a CUDA graph on its own stream, so
 // everything that changes from ply to ply is read from this device-resident record instead of being a kernel argument.
@@ -604,7 +627,8 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
 template <class G>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
-                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr, unsigned char* s_root = nullptr) {
+                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr, unsigned char* s_root = nullptr,
+                      unsigned char* s_cache_row = nullptr, const int nc_nodes = 0) {
   const long long tr0 = tr ? clock64() : 0;
   typedef Layout<G> Lay;
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
@@ -678,6 +702,14 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
             *reinterpret_cast<float4*>(nrec + Lay::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
+#if AG_TREE_SMEM
+          if (s_cache_row != nullptr && nd < nc_nodes) {                              // write-through: π̄ of a cached node
+#pragma unroll
+            for (int c = 0; c < AP / 4; c++)
+              *reinterpret_cast<float4*>(s_cache_row + nd * RootSlot<AP>::BYTES + RootSlot<AP>::OFF_POLICY + 16 * c) =
+                  make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
+          }
+#endif
 #if AG_ROOT_SMEM
           if (s_root != nullptr && jj == 0) {                                        // the root: the next descent starts from this copy
             *reinterpret_cast<uint2*>(s_root) = hdr_w;
@@ -727,10 +759,15 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
     u64 cw0, cw1 = 0;
     float pol[AP];
-#if AG_ROOT_SMEM
-    if (depth == 0 && rollout >= 2 && SH.root != nullptr) {
-      // the root as the backup phase of this rollout left it in shared memory (RootSlot)
-      const unsigned char* sl = SH.root + (gl >> 7) * SH.root_tile_stride + (gl & 127) * RootSlot<AP>::BYTES;
+#if AG_TREE_SMEM || AG_ROOT_SMEM
+#if AG_TREE_SMEM
+    unsigned char* const csl = node_cache_slot<G>(SH, gl, node);                       // this node's cache entry, if it has one
+    const unsigned char* sl = csl;
+#else
+    // the root as the backup phase of this rollout left it in shared memory (RootSlot)
+    const unsigned char* sl = (depth == 0 && rollout >= 2 && SH.root != nullptr) ? SH.root + (gl >> 7) * SH.root_tile_stride + (gl & 127) * RootSlot<AP>::BYTES : nullptr;
+#endif
+    if (sl != nullptr) {
       hw = *reinterpret_cast<const uint2*>(sl);
       const uint2 cv = *reinterpret_cast<const uint2*>(sl + RootSlot<AP>::OFF_CHILD);
       cw0 = (u64)cv.x | ((u64)cv.y << 32);
@@ -820,6 +857,17 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
       NodeHdr nh; nh.parent = (uint8_t)(node + 1); nh.action = (uint8_t)(best + 1); nh.nchild = 0;
       nh.flags = term ? F_TERMINAL : 0; nh.result = (int8_t)res; nh.pad[0] = nh.pad[1] = nh.pad[2] = 0;
       *reinterpret_cast<NodeHdr*>(nrec + Lay::OFF_HDR) = nh;
+#if AG_TREE_SMEM
+      if (csl != nullptr) {                                                            // the parent's entry: child id and child count
+        csl[RootSlot<AP>::OFF_CHILD + best] = (uint8_t)c;
+        csl[2] = (uint8_t)(nchild + 1);                                                // NodeHdr::nchild
+      }
+      if (unsigned char* nsl = node_cache_slot<G>(SH, gl, c - 1)) {                    // the new node's entry (π̄ is written by expand)
+        *reinterpret_cast<NodeHdr*>(nsl) = nh;
+#pragma unroll
+        for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint2*>(nsl + RootSlot<AP>::OFF_CHILD + 8 * k) = make_uint2(0, 0);
+      }
+#endif
       SH.state[gl] = ns;
       SH.hdr[gl] = nh;
       node = c - 1;
@@ -920,6 +968,14 @@ AG_D LeafEval expand_game1(const SearchParams& P, const int g, const int gl, con
       for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pr[a];
     }
     reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
+#if AG_TREE_SMEM
+    if (unsigned char* sl = node_cache_slot<G>(SH, gl, leaf)) {                          // write-through: π̄ = prior, expanded flag
+#pragma unroll
+      for (int c = 0; c < AP / 4; c++)
+        *reinterpret_cast<float4*>(sl + RootSlot<AP>::OFF_POLICY + 16 * c) = make_float4(pr[4 * c], pr[4 * c + 1], pr[4 * c + 2], pr[4 * c + 3]);
+      sl[3] = (uint8_t)(h.flags | F_EXPANDED);                                           // NodeHdr::flags
+    }
+#endif
   }
   LeafEval E;
   E.v = v; E.term = term ? 1 : 0; E.parent = h.parent; E.action = h.action;
