@@ -161,6 +161,9 @@ struct RolloutShared {
 #ifndef AG_TREE_SMEM
 #define AG_TREE_SMEM 0
 #endif
+#ifndef AG_DESC_LD128
+#define AG_DESC_LD128 0
+#endif
 #if AG_TREE_SMEM && AG_ROOT_SMEM
 #error "AG_TREE_SMEM subsumes AG_ROOT_SMEM: enable one of them"
 #endif
@@ -783,9 +786,18 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     } else
 #endif
     {
-      hw = hot_ld_u2(rec + Lay::OFF_HDR);
       // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
+#if AG_DESC_LD128
+      // development variant (not yet run on a GPU): header and the first child word are the record's first 16 bytes — one 128-bit
+      // request instead of two 64-bit ones (the descent at full load is bound by the SM's load-request throughput)
+      static_assert(Lay::OFF_HDR % 16 == 0 && Lay::OFF_CHILD == Lay::OFF_HDR + 8, "header and child ids are adjacent");
+      const uint4 hc = hot_ld_u4(rec + Lay::OFF_HDR);
+      hw = make_uint2(hc.x, hc.y);
+      const uint2 cv = make_uint2(hc.z, hc.w);
+#else
+      hw = hot_ld_u2(rec + Lay::OFF_HDR);
       const uint2 cv = hot_ld_u2(rec + Lay::OFF_CHILD);
+#endif
       cw0 = (u64)cv.x | ((u64)cv.y << 32);
       if (AP == 16) {
         const uint2 cv1 = hot_ld_u2(rec + Lay::OFF_CHILD + 8);
