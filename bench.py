@@ -307,9 +307,10 @@ def main():
         "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                      "peak_source": peak_src, "bytes_per_sim": bytes_sim, "avg_launch_us": 1e3 * dom_ms / classes[dom]["launches"],
                      "share_of_step": dom_ms / total_ms, "sims_per_launch": pst["sims"] / classes[dom]["launches"],
-                     "note": "latency-bound, not HBM-bound: see DESIGN.md §6 and profiles/ (DRAM throughput ~9% of peak, issue slots ~30% busy, "
-                             "26 of 32 lanes active, stalls on the global-load scoreboard and the phase barriers; the per-rollout dependent chain — "
-                             "global round trips of the descent, the Newton solve and the 7-layer MMA chain — sets a floor independent of the number of live games)"},
+                     "note": "latency-bound, not HBM-bound: see DESIGN.md §6b and profiles/ncu_dominant_kernel.json (full-L launch: DRAM throughput 7 % of peak, "
+                             "issue slots 30 % busy, 27 of 32 lanes active, L2 hit rate 73 %, stalls on the phase barriers and the global-load scoreboard); 54 % of a "
+                             "generation is spent in plies with more than 128 games per SM, bound by what the games of an SM share, 43.5 % in the tail, where a rollout "
+                             "is a dependent chain — descent round trips, the Newton solve, 8 dependent MMA layers — whose length does not shrink with the number of live games"},
         "roofline_nn": {"kernel": nn_name, "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
                         "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
