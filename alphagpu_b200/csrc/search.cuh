@@ -164,6 +164,21 @@ struct RolloutShared {
 #ifndef AG_DESC_LD128
 #define AG_DESC_LD128 0
 #endif
+// -DAG_PREFETCH=1 (development variant, NOT YET RUN ON A GPU): the full-load plies are bound by DRAM latency on L2 misses (live trees
+// 268 MB against 126 MB of L2, L2 hit rate 73 %) while DRAM bandwidth sits at 7 % — so spend bandwidth on lead time:
+//  - the backup item of a path node prefetches (to L2) the descent fields of all its children: the next descent, a whole network phase
+//    later, leaves the old path through one of them;
+//  - the descent prefetches the rest of every record it passes (visit counts, prior, q: bytes 64..REC), which its backup reads next.
+#ifndef AG_PREFETCH
+#define AG_PREFETCH 0
+#endif
+AG_D void prefetch_l2(const void* a) {
+#if AG_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+#else
+  (void)a;
+#endif
+}
 #if AG_TREE_SMEM && AG_ROOT_SMEM
 #error "AG_TREE_SMEM subsumes AG_ROOT_SMEM: enable one of them"
 #endif
@@ -672,6 +687,10 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
         }
+#if AG_PREFETCH
+#pragma unroll
+        for (int a = 0; a < A; a++) if (ch[a] != 0) prefetch_l2(gbase + (size_t)(ch[a] - 1) * REC);
+#endif
 #if AG_ROOT_SMEM
         const uint2 hdr_w = hot_ld_u2(nrec + Lay::OFF_HDR);
         const int nchild = (int)((hdr_w.x >> 16) & 0xFFu);
@@ -809,6 +828,10 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
         pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
       }
     }
+#if AG_PREFETCH
+#pragma unroll
+    for (int o = 64; o < REC; o += 64) prefetch_l2(rec + o);                          // what this node's backup item will read
+#endif
     // the uniform of this depth does not depend on the loads above: Philox runs while they are in flight
     const long long tP0 = (tr && depth == 0) ? clock64() : 0;
     if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
