@@ -19,6 +19,15 @@ namespace ag {
 namespace fused {
 using namespace tc;
 
+// -DAG_NHALF=1 (development variant, NOT YET RUN ON A GPU): with 8 warps per tile a trunk layer in the ordinary orientation is issued as
+// two chains of 8 MMAs, output columns 0..63 and 64..127 (two barriers), and every warp owns one 32-column slice in EACH half: it runs
+// the TMEM loads, the arithmetic and the residual store of its first slice while the tensor core still works on the second half; the
+// operands computed from the first slice are stored only once that second chain — which reads the same tile as its A operand — is done.
+// Every column is accumulated over K in the same order as before, so the results are bit-identical.
+#ifndef AG_NHALF
+#define AG_NHALF 0
+#endif
+
 // NT = tiles per CTA.  NT = 2: 1024 threads, one CTA per SM, 3-stage weight ring.  NT = 1: 512 threads, 2-stage ring, TWO CTAs per
 // SM (98 KB shared memory, 256 TMEM columns, 64 registers each): while one CTA waits on its MMA chain the other's search phase
 // uses the issue slots.
@@ -158,10 +167,17 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
+#if AG_NHALF
+  constexpr bool NHALF = CPW == 2;                                     // only where a warp owns a slice in each column half
+  const uint32_t bar_done2 = smem_u32(bars + 74);                      // [2] all MMAs of the layer (the 48 bytes behind sbias are free)
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, ntiles); }
     for (int t = 0; t < NT; t++) mbar_init(bar_done + 8 * t, 1);
+#if AG_NHALF
+    if (NHALF) for (int t = 0; t < NT; t++) mbar_init(bar_done2 + 8 * t, 1);
+#endif
     mbar_init(bar_stagger, 1);
     fence_barrier_init();
   }
@@ -346,7 +362,28 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
               const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
               umma_bf16(tmem_acc_u, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
             }
-          } else {
+          }
+#if AG_NHALF
+          else if (NHALF && !is_head) {
+            const uint32_t idesc = umma_idesc<FMT>(TC_N / 2);           // 64 output columns per chain
+#pragma unroll
+            for (int ks = 0; ks < TC_N / 16; ks++) {
+              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+              umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar_done + 8 * t_u);                             // columns 0..63 are complete
+            const uint64_t brow = (uint64_t)(((TC_N / 2) * 128) >> 4);   // weight rows 64..127: 8 swizzle atoms further in each K tile
+#pragma unroll
+            for (int ks = 0; ks < TC_N / 16; ks++) {
+              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+              umma_bf16(tmem_acc_u + (uint32_t)(TC_N / 2), ad0 + ainc, bd0 + brow + binc, idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar_done2 + 8 * t_u);                            // all of the layer's MMAs
+          }
+#endif
+          else {
             const uint32_t idesc = umma_idesc<FMT>(nl);
 #pragma unroll
             for (int ks = 0; ks < TC_N / 16; ks++) {
@@ -355,7 +392,12 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
               umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
             }
           }
+#if AG_NHALF
+          // unsplit layers (head, swapped) complete both barriers at once, so that both advance one phase per layer
+          if (!(NHALF && !is_head && !(SW && swapped))) { umma_commit(bar_done + 8 * t_u); if (NHALF) umma_commit(bar_done2 + 8 * t_u); }
+#else
           umma_commit(bar_done + 8 * t_u);
+#endif
           if (NT == 2) umma_commit(bar_empty + 8 * s);                  // one tile: the requesting lane has itself seen the previous layer complete
           if (wl == 0 && t_u == 0) umma_commit(bar_stagger);
         }
@@ -366,6 +408,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
       // the request sat on the critical path: 2 k cycles per rollout)
       if (warp == 1 && lane == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
       mbar_wait(bar_done + 8 * t, wl & 1);
+#if AG_NHALF
+      const bool split = NHALF && !is_head && !(SW && swapped);         // CTA-uniform: this layer was issued as two column halves
+      if (NHALF && !split) mbar_wait(bar_done2 + 8 * t, wl & 1);        // keeps the second barrier's phase in step on unsplit layers
+#endif
       tc_fence_after();
       long long lt3 = 0;
       if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
@@ -386,6 +432,53 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
       } else if (!is_head) {
         // epilogue: b = relu(acc) (base) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b)
         const bool keep = (l + 2 < nlayers);                            // the last trunk layer's residual is not read again
+#if AG_NHALF
+        uint4 pend[4];                                                  // operands of a first-half slice, held back
+        int pend_cs = -1;
+        bool waited2 = !split;
+        auto flush_pending = [&] {
+          if (!waited2) { mbar_wait(bar_done2 + 8 * t, wl & 1); tc_fence_after(); waited2 = true; }
+          if (pend_cs >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int c = 4 * pend_cs + q;
+              *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pend[q];
+            }
+            pend_cs = -1;
+          }
+        };
+#pragma unroll
+        for (int ji = 0; ji < 2 * CPW; ji++) {
+          // slices of this warp: one in each column half when the layer is split, else csb, csb + 1
+          const int cs = NHALF ? (csb >> 1) + 2 * (ji >> 1) : csb + (ji >> 1);
+          const int i = ji & 1;
+          const bool hold = split && cs < 2;                            // a slice of the first half: its stores wait
+          if (split && !hold) flush_pending();                          // first touch of the second half: wait for its MMAs
+          const uint32_t lane_sel = lane_row + (uint32_t)(cs * 32);
+          uint32_t va[16], vh[16];
+          tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
+          if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; e++) {
+            const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
+            const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
+            vh[e] = __float_as_uint(hv);
+          }
+          if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh);
+#pragma unroll
+          for (int c2 = 0; c2 < 2; c2++) {
+            const int c = 4 * cs + 2 * i + c2;
+            const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[8 * c2 + 0]), __uint_as_float(vh[8 * c2 + 1])),
+                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 2]), __uint_as_float(vh[8 * c2 + 3])),
+                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 4]), __uint_as_float(vh[8 * c2 + 5])),
+                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 6]), __uint_as_float(vh[8 * c2 + 7])));
+            if (hold) { pend[2 * i + c2] = pk; pend_cs = cs; }
+            else *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
+          }
+        }
+        flush_pending();
+#else
 #pragma unroll
         for (int ji = 0; ji < 2 * CPW; ji++) {
           const int cs = csb + (ji >> 1), i = ji & 1;
@@ -411,6 +504,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
             *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
           }
         }
+#endif
         tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
