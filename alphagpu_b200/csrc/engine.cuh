@@ -97,6 +97,11 @@ struct EngineT : EngineBase {
   static constexpr int A = G::A;
 
   cudaStream_t stream = nullptr;
+  // AGPU_STREAM_SAMPLES=1 (development switch, NOT YET RUN ON A GPU): the rows a ply appends to the sample arrays (state, policy, player,
+  // game, ply — final when pushed) are copied to the caller's buffers on a second stream while the next ply searches; only value and
+  // fstate, which need the game's end, are copied after the loop (26 of 96 MB at the bench size)
+  cudaStream_t copy_stream = nullptr;
+  bool stream_samples = false;
   int64_t L_cap = 0;
   int R = 0;
   int64_t L_live = 0;
@@ -167,6 +172,7 @@ struct EngineT : EngineBase {
     if (total_host) cudaFreeHost(total_host);
     if (tallies_host) cudaFreeHost(tallies_host);
     if (stream) cudaStreamDestroy(stream);
+    if (copy_stream) cudaStreamDestroy(copy_stream);
   }
 
   // ---- launch bracket: counts launches, optionally times them with events on the library stream ----
@@ -214,6 +220,8 @@ struct EngineT : EngineBase {
     AG_REQUIRE(cfg.device >= 0 && cfg.device < ndev, AGPU_ERR_INVALID, "device ordinal out of range");
     AG_CK(cudaSetDevice(cfg.device));
     AG_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("AGPU_STREAM_SAMPLES")) stream_samples = atoi(e) != 0;
+    if (stream_samples) AG_CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     L_cap = cfg.max_games; R = cfg.rollouts;
     AG_CK(tree.ensure((size_t)L_cap * R * Lay::REC));
     AG_CK(nnodes.ensure(L_cap)); AG_CK(leaf.ensure(L_cap)); AG_CK(uid.ensure(L_cap)); AG_CK(uid_b.ensure(L_cap));
@@ -798,6 +806,8 @@ struct EngineT : EngineBase {
     double t_prev = 0;
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     if (trace_plies) t_prev = now_ms();
+    const bool streaming = stream_samples && !duel && samples != nullptr && samples->capacity > 0;
+    if (streaming) AG_REQUIRE(samples->state && samples->policy && samples->player && samples->value && samples->fstate, AGPU_ERR_INVALID, "null sample array");
     while (L > 0) {
       const int actor = duel ? ((round % 2 == 0) ? slot : slot_b) : slot;                  // :592-596
       int rc = use_fused ? enqueue_search_fused(L, actor, visits, duel ? 0 : 1, cpuct, seed, round)                     // mcts_single (:503, :599)
@@ -812,6 +822,17 @@ struct EngineT : EngineBase {
       launch(K_COMPACT, [&] { compact_kernel<G><<<nb, 256, 0, stream>>>(P, (int)L, Y, st_b.p, uid_b.p); });
       AG_CK(cudaMemcpyAsync(total_host, total_dev.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
       AG_CK(cudaStreamSynchronize(stream));                                                  // one host sync per ply (the reference: 6·R+3)
+      if (streaming) {                                                                       // this ply's rows [count, count + L) are final
+        const long long lo = count, hi = std::min<long long>(count + L, std::min<long long>(samples->capacity, cap));
+        if (hi > lo) {
+          const size_t n = (size_t)(hi - lo);
+          AG_CK(cudaMemcpyAsync(samples->state + lo * 2 * G::VS, s_state.p + lo * 2 * G::VS, n * 2 * G::VS, cudaMemcpyDeviceToHost, copy_stream));
+          AG_CK(cudaMemcpyAsync(samples->policy + lo * A, s_policy.p + lo * A, sizeof(float) * n * A, cudaMemcpyDeviceToHost, copy_stream));
+          AG_CK(cudaMemcpyAsync(samples->player + lo, s_player.p + lo, n, cudaMemcpyDeviceToHost, copy_stream));
+          if (samples->game) AG_CK(cudaMemcpyAsync(samples->game + lo, s_game.p + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, copy_stream));
+          if (samples->ply) AG_CK(cudaMemcpyAsync(samples->ply + lo, s_ply.p + lo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, copy_stream));
+        }
+      }
       if (trace_plies) { const double t = now_ms(); fprintf(stderr, "ply %u L %lld ms %.3f us/rollout %.2f\n", round, (long long)L, t - t_prev, 1e3 * (t - t_prev) / visits); t_prev = t; }
       count += L;
       L = *total_host;
@@ -838,14 +859,19 @@ struct EngineT : EngineBase {
       const long long rows = std::min<long long>(count, std::min<long long>(samples->capacity, cap));
       if (rows > 0) {
         AG_REQUIRE(samples->state && samples->policy && samples->player && samples->value && samples->fstate, AGPU_ERR_INVALID, "null sample array");
-        AG_CK(cudaMemcpyAsync(samples->state, s_state.p, (size_t)rows * 2 * G::VS, cudaMemcpyDeviceToHost, stream));
-        AG_CK(cudaMemcpyAsync(samples->policy, s_policy.p, sizeof(float) * rows * A, cudaMemcpyDeviceToHost, stream));
-        AG_CK(cudaMemcpyAsync(samples->player, s_player.p, rows, cudaMemcpyDeviceToHost, stream));
+        if (!streaming) {
+          AG_CK(cudaMemcpyAsync(samples->state, s_state.p, (size_t)rows * 2 * G::VS, cudaMemcpyDeviceToHost, stream));
+          AG_CK(cudaMemcpyAsync(samples->policy, s_policy.p, sizeof(float) * rows * A, cudaMemcpyDeviceToHost, stream));
+          AG_CK(cudaMemcpyAsync(samples->player, s_player.p, rows, cudaMemcpyDeviceToHost, stream));
+        }
         AG_CK(cudaMemcpyAsync(samples->value, s_value.p, sizeof(float) * rows, cudaMemcpyDeviceToHost, stream));
         AG_CK(cudaMemcpyAsync(samples->fstate, s_fstate.p, (size_t)rows * G::FS, cudaMemcpyDeviceToHost, stream));
-        if (samples->game) AG_CK(cudaMemcpyAsync(samples->game, s_game.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream));
-        if (samples->ply) AG_CK(cudaMemcpyAsync(samples->ply, s_ply.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream));
+        if (!streaming) {
+          if (samples->game) AG_CK(cudaMemcpyAsync(samples->game, s_game.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream));
+          if (samples->ply) AG_CK(cudaMemcpyAsync(samples->ply, s_ply.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream));
+        }
         AG_CK(cudaStreamSynchronize(stream));
+        if (streaming) AG_CK(cudaStreamSynchronize(copy_stream));
       }
     }
     if (profiling) harvest();
