@@ -78,11 +78,27 @@ AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v
 // lane f and game n in column n.  This thread owns feature 32*wq + lane and the NC games of slice cs; it applies relu / the
 // residual, keeps the fp32 stream in TMEM (same transposed shape) and scatters the 16-bit operand of the next layer into the
 // ordinary games x features, K-major, 128B-swizzled tile (so the head layer and the encoder need no second layout).
+// -DAG_SWAP_RESREG=1 (development variant, NOT YET RUN ON A GPU): in the swapped orientation a thread owns the same NC (8 or 16) residual
+// values in every layer, so they can stay in registers (sres) instead of making a TMEM round trip per layer (tcgen05.ld + st + wait::st).
+#ifndef AG_SWAP_RESREG
+#define AG_SWAP_RESREG 0
+#endif
 template <int FMT, int NC>
-AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs, int lane, int l, bool keep, unsigned char* At) {
+AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs, int lane, int l, bool keep, unsigned char* At, uint32_t (&sres)[16]) {
   uint32_t va[NC], vh[NC];
   const uint32_t taddr = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * NC);
   tmem_ldn(tmem_acc + taddr, va);
+#if AG_SWAP_RESREG
+  (void)tmem_res; (void)keep;
+  tmem_ld_wait();
+#pragma unroll
+  for (int e = 0; e < NC; e++) {
+    const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
+    const float hv = (l == 0) ? ra : __uint_as_float(sres[e]) + ra;
+    sres[e] = vh[e] = __float_as_uint(hv);
+  }
+#else
+  (void)sres;
   if (l > 0) tmem_ldn(tmem_res + taddr, vh);
   tmem_ld_wait();
 #pragma unroll
@@ -92,6 +108,7 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs,
     vh[e] = __float_as_uint(hv);
   }
   if (keep) tmem_stn(tmem_res + taddr, vh);
+#endif
   const int f = 32 * wq + lane;
   unsigned char* base = At + (f >> 6) * TC_KTILE_BYTES_A + (f & 7) * 2;
   const int c = (f & 63) >> 3;
@@ -338,6 +355,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
     fence_proxy_async();
     named_bar_sync(1 + t, 32 * WPT);
 
+    uint32_t sres[16];                                                 // AG_SWAP_RESREG: this thread's residual values (swapped orientation)
     for (int l = 0; l < nlayers; l++, wl++) {
       const int s = wl % STAGES;
       const bool is_head = (l == nlayers - 1);
@@ -419,8 +437,8 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
       if (SW && swapped && !is_head) {
         const bool keep = (l + 2 < nlayers);
         if constexpr (SW) {
-          if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At);
-          else epilogue_swapped<FMT, 16>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At);
+          if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At, sres);
+          else epilogue_swapped<FMT, 16>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At, sres);
         }
         tmem_st_wait();
         tc_fence_before();
