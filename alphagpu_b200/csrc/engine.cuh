@@ -81,6 +81,10 @@ struct DevBuf {
     return e;
   }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }              // temporaries of forward / game_ops / ... are freed on every early return
 };
 
 struct NetSlot {
@@ -118,6 +122,7 @@ struct EngineT : EngineBase {
   DevBuf<uint8_t> path_node, path_move, path_len;
   float last_cpuct = 2.0f;   // cpuct of the most recent descent: the backup re-solves π̄ with it (FAST layouts)
   int32_t* total_host = nullptr;   // pinned
+  unsigned long long* fault_host = nullptr;   // pinned: tallies[4] of the ply just played ("faute", mcts_gpu.jl:526-529)
   unsigned long long* tallies_host = nullptr;
   NetSlot nets[2];
   // samples
@@ -143,9 +148,6 @@ struct EngineT : EngineBase {
   int fused_wpt = 8;               // warps per tile of the two-tile variant: 8 = 512 threads x 128 registers (16: 1024 x 64, 91 vs 84 ms)
   int fused_swap_max = 128;        // games per CTA up to which the 512-thread variant is launched
   int num_sms = 148, fused_min_gpc = 8, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
-  // DUAL: above fused_dual_min games per SM the ply runs as one-tile CTAs of 256 threads x 128 registers, two per SM (fused.cuh: FCfg::DUAL)
-  bool fused_dual = false;
-  int fused_dual_min = 129, fused_dual_stagger_us = 0;
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -170,6 +172,7 @@ struct EngineT : EngineBase {
     for (auto& n : nets) { n.base.release(); n.res.release(); n.pol_w.release(); n.pol_b.release(); n.val_w.release(); n.val_b.release(); n.tc_bias.release(); n.tc_img.release(); }
     s_state.release(); s_player.release(); s_fstate.release(); s_policy.release(); s_value.release(); s_game.release(); s_ply.release();
     if (total_host) cudaFreeHost(total_host);
+    if (fault_host) cudaFreeHost(fault_host);
     if (tallies_host) cudaFreeHost(tallies_host);
     if (stream) cudaStreamDestroy(stream);
     if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -232,6 +235,7 @@ struct EngineT : EngineBase {
     AG_CK(path_node.ensure((size_t)L_cap * R)); AG_CK(path_move.ensure((size_t)L_cap * R)); AG_CK(path_len.ensure(L_cap));
     AG_CK(cudaMemsetAsync(path_len.p, 0, L_cap, stream));
     AG_CK(cudaMallocHost((void**)&total_host, sizeof(int32_t)));
+    AG_CK(cudaMallocHost((void**)&fault_host, sizeof(unsigned long long)));
     AG_CK(cudaMallocHost((void**)&tallies_host, 8 * sizeof(unsigned long long)));
     AG_CK(cudaMemsetAsync(tree.p, 0, (size_t)L_cap * R * Lay::REC, stream));
     AG_CK(cudaMemsetAsync(policy_final.p, 0, (size_t)L_cap * A * sizeof(float), stream));
@@ -261,21 +265,6 @@ struct EngineT : EngineBase {
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
         if (const char* e = getenv("AGPU_FUSED_WPT")) fused_wpt = atoi(e) == 8 ? 8 : 16;
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1, 8>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1, 8>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, false, 8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        if (const char* e = getenv("AGPU_FUSED_DUAL")) fused_dual = atoi(e) != 0;
-        if (const char* e = getenv("AGPU_FUSED_DUAL_MIN")) fused_dual_min = atoi(e);
-        if (const char* e = getenv("AGPU_FUSED_DUAL_STAGGER_US")) fused_dual_stagger_us = atoi(e);
-        if (getenv("AGPU_DEBUG")) {                                     // development: resident CTAs per SM of the per-ply kernel variants
-          int occ_dual = 0, occ_two = 0, occ_sw = 0;
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_dual, fused::ply_kernel<G, 1, 1, false, 8>, fused::FCfg<1, 8>::THREADS, fused::FCfg<1, 8>::SMEM);
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_two, fused::ply_kernel<G, 1, 2, false, 8>, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM);
-          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_sw, fused::ply_kernel<G, 1, 1, true>, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM);
-          fprintf(stderr, "[agpu] ply_kernel CTAs per SM: dual %d (smem %d), two-tile %d (smem %d), small-batch %d (smem %d); dual=%d dual_min=%d\n",
-                  occ_dual, fused::FCfg<1, 8>::SMEM, occ_two, fused::FCfg<2, 8>::SMEM, occ_sw, fused::FCfg<1>::SMEM, (int)fused_dual, fused_dual_min);
-        }
         if (const char* e = getenv("AGPU_FUSED_SWAP")) fused_swap = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_SWAP_MAX")) fused_swap_max = atoi(e);
         use_fused = true;
@@ -305,22 +294,10 @@ struct EngineT : EngineBase {
       gpc = (gpc + 7) / 8 * 8;
       if (gpc < fused_min_gpc) gpc = fused_min_gpc;
       if (gpc > cap) gpc = cap;
-      // DUAL: enough games per SM to fill two one-tile CTAs -> spread them over 2 CTA slots per SM instead
-      const bool dual = fused_dual && fused_tiles == 2 && gpc >= fused_dual_min;
-      if (dual) {
-        S.pad = fused_dual_stagger_us;
-        gpc = (int)((L + 2 * num_sms - 1) / (2 * num_sms));
-        gpc = (gpc + 7) / 8 * 8;
-        if (gpc < fused_min_gpc) gpc = fused_min_gpc;
-        if (gpc > 128) gpc = 128;
-      }
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (dual) {
-          if (fmt == 0) fused::ply_kernel<G, 0, 1, false, 8><<<grid, fused::FCfg<1, 8>::THREADS, fused::FCfg<1, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 1, false, 8><<<grid, fused::FCfg<1, 8>::THREADS, fused::FCfg<1, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
-        } else if (gpc <= fused_swap_max && fused_swap) {
+        if (gpc <= fused_swap_max && fused_swap) {
           // the tail of a generation: few games per CTA -> the 512-thread, 128-register, swapped-orientation variant
           if (fmt == 0) fused::ply_kernel<G, 0, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
@@ -785,8 +762,9 @@ struct EngineT : EngineBase {
     PlyState Y; Y.next_state = st_a.p; Y.alive = alive.p; Y.block_count = block_count.p; Y.game_result = game_result.p; Y.game_final = game_final.p;
     Y.tallies = tallies.p;
 
-    cudaEvent_t ev0, ev1;
-    AG_CK(cudaEventCreate(&ev0)); AG_CK(cudaEventCreate(&ev1));
+    struct EvPair { cudaEvent_t a = nullptr, b = nullptr; ~EvPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evp;
+    AG_CK(cudaEventCreate(&evp.a)); AG_CK(cudaEventCreate(&evp.b));
+    const cudaEvent_t ev0 = evp.a, ev1 = evp.b;
     const int64_t launches0 = launch_count;
     AG_CK(cudaEventRecord(ev0, stream));
     AG_CK(cudaMemsetAsync(tallies.p, 0, 8 * sizeof(unsigned long long), stream));
@@ -802,6 +780,7 @@ struct EngineT : EngineBase {
     L_live = ngames;
     int64_t L = ngames, sims = 0, npos = 0, count = 0;
     uint32_t round = 0;
+    bool aborted = false;
     const bool trace_plies = getenv("AGPU_TRACE_PLIES") != nullptr;   // development: per-ply wall time on stderr
     double t_prev = 0;
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
@@ -821,6 +800,7 @@ struct EngineT : EngineBase {
       launch(K_COMPACT, [&] { scan_blocks_kernel<<<1, 1024, 0, stream>>>(block_count.p, nb, total_dev.p); });
       launch(K_COMPACT, [&] { compact_kernel<G><<<nb, 256, 0, stream>>>(P, (int)L, Y, st_b.p, uid_b.p); });
       AG_CK(cudaMemcpyAsync(total_host, total_dev.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+      AG_CK(cudaMemcpyAsync(fault_host, tallies.p + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
       AG_CK(cudaStreamSynchronize(stream));                                                  // one host sync per ply (the reference: 6·R+3)
       if (streaming) {                                                                       // this ply's rows [count, count + L) are final
         const long long lo = count, hi = std::min<long long>(count + L, std::min<long long>(samples->capacity, cap));
@@ -837,6 +817,11 @@ struct EngineT : EngineBase {
       count += L;
       L = *total_host;
       round += 1;
+      // "faute" (mcts_gpu.jl:526-529, :611-614): the reference stops the generation at the first illegal move and returns valid=false.
+      // Here the ply that produced it is completed (all its games in one launch) and the loop ends; the call returns
+      // AGPU_ERR_ILLEGAL_MOVE with the samples pushed so far.  Without this a degenerate policy (NaN weights) never terminates:
+      // an illegal Connect4 move leaves the position unchanged.  The ply cap is a second guard for plug-in games.
+      if (*fault_host != 0 || round > (uint32_t)G::MAXLEN + 8) { aborted = true; break; }
       if (L > 0) launch(K_BEGIN, [&] { root_reset_kernel<G><<<blocks_for_threads(L), 256, 0, stream>>>(P, (int)L, st_b.p, uid_b.p); });   // re_init (:557-561)
       L_live = L;
     }
@@ -848,7 +833,6 @@ struct EngineT : EngineBase {
     AG_CK(cudaGetLastError());
     float ms = 0.f;
     AG_CK(cudaEventElapsedTime(&ms, ev0, ev1));
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     results[0] = (int64_t)tallies_host[0]; results[1] = (int64_t)tallies_host[1]; results[2] = (int64_t)tallies_host[2];
     if (stats) {
       stats->sims = sims; stats->positions = npos; stats->plies = round; stats->total_length = (int64_t)tallies_host[3];
@@ -875,7 +859,12 @@ struct EngineT : EngineBase {
       }
     }
     if (profiling) harvest();
-    return stats && stats->faults ? AGPU_ERR_ILLEGAL_MOVE : AGPU_OK;
+    if (aborted || tallies_host[4] != 0) {
+      err = tallies_host[4] != 0 ? "illegal move chosen from the search policy (\"faute\", mcts_gpu.jl:526-529): generation stopped"
+                                 : "ply cap exceeded: games do not terminate";
+      return AGPU_ERR_ILLEGAL_MOVE;
+    }
+    return AGPU_OK;
   }
 
   int profile(int enable) override {

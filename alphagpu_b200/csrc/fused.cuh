@@ -35,12 +35,8 @@ template <int NT, int WPT = 16> struct FCfg {
   static constexpr int THREADS = 32 * WPT * NT;                        // WPT warps per tile: 16 (one 32-column slice per warp) or 8 (two)
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  // DUAL (one tile, 8 warps): 256 threads x 128 registers and 112.5 KB of shared memory, so that TWO CTAs share an SM
-  // (2 x (112.5 + 1 reserved) KB = 227 of 228 KB, 2 x 256 TMEM columns, 2 x 256 x 128 registers): the two CTAs drift apart and one's
-  // search phase (latency chains, few issue slots) runs under the other's network phase.  The work area below is trimmed by 1 KB for it.
-  static constexpr bool DUAL = (NT == 1 && WPT == 8);
   static constexpr int ITEM_MAP = 1024;                                // backup items whose game is looked up in a byte map
-  static constexpr int WORK = (DUAL ? 1024 : 2048) + GAMES * (44 + 72); // barriers/bias/backup work list + rollout hand-off
+  static constexpr int WORK = 2048 + GAMES * (44 + 72); // barriers/bias/backup work list + rollout hand-off
   static constexpr int WORK_USED = 640 + GAMES * 32 + GAMES * 4 + (GAMES + 1) * 4 + 16 + GAMES * 68 + ITEM_MAP;   // as laid out in the kernel
   static_assert(WORK_USED <= WORK, "shared-memory work area overflows its budget");
   // AG_TREE_SMEM (KB): node cache of the one-tile, 16-warp kernels (the small-batch variant of the tail), after the work area
@@ -49,7 +45,6 @@ template <int NT, int WPT = 16> struct FCfg {
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
   static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
 };
-static_assert(2 * (FCfg<1, 8>::SMEM + 1024) <= 228 * 1024, "two DUAL CTAs (plus 1 KB reserved each) must fit the SM's 228 KB");
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
   asm volatile(
@@ -123,7 +118,7 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs,
 // SW: the small-batch variant (host: games per CTA <= 128): one tile, 512 threads, one CTA per SM — 128 registers per thread instead
 // of 64 — and, up to 64 games, the trunk layers in the swapped orientation (below).
 template <class G, int FMT, int NT, bool SW = false, int WPT = 16>
-__global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 2 : (SW || WPT == 8) ? 1 : FCfg<NT, WPT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+__global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 : FCfg<NT, WPT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   static_assert(!SW || (NT == 1 && WPT == 16), "the swapped variant runs a single tile with 16 warps");
   static_assert(WPT == 16 || WPT == 8, "warps per tile");
   typedef Layout<G> Lay;
@@ -172,13 +167,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
   // expand reads the outputs in between.  (Staying under 196 KB of shared memory keeps the next carve-out step — 32 KB of L1 — free.)
   SH.out = reinterpret_cast<float*>(sA);
   SH.out_tile_stride = TC_A_BYTES / 4;
-  // ... and so does the root's descent view (search.cuh: RootSlot), in the second half of the same idle buffer
-  SH.root = AG_ROOT_SMEM ? sA + TC_A_BYTES / 2 : nullptr;
-  SH.root_tile_stride = TC_A_BYTES;
   // node cache (AG_TREE_SMEM): the first nc_nodes nodes of each of this CTA's games; the fewer games, the deeper the cache
   SH.nc_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sW + STAGES * TC_W_STAGE_BYTES + C::WORK) + 15) & ~uintptr_t(15));
   SH.nc_nodes = C::TREE_BYTES > 0 ? min(P.R, (C::TREE_BYTES - 16) / (RootSlot<Lay::APAD>::BYTES * count)) : 0;
-  static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_A_BYTES / 2 && TC_TILE_M * RootSlot<Lay::APAD>::BYTES <= TC_A_BYTES / 2, "outputs and root slots share the idle A tile");
+  static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_A_BYTES, "the network's outputs live in the idle A tile");
   static_assert(sizeof(typename G::State) + 8 + 1 + 2 * PATH_SMEM_DEPTH <= 68, "rollout hand-off budget per game");
   static_assert(FCfg<2>::SMEM <= 195 * 1024, "shared memory beyond the 196 KB carve-out costs 32 KB of L1");
 
@@ -264,13 +256,6 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
   }
 #endif
 
-  // DUAL, optional (S.pad = microseconds): the second half of the grid — the CTAs that land as second residents of their SMs — starts
-  // late by about half a rollout, so that the two residents begin in opposite phases instead of finding them by contention
-  if (C::DUAL && S.pad > 0 && (int)blockIdx.x >= ((int)gridDim.x + 1) / 2) {
-    const long long until = clock64() + (long long)S.pad * 1965;
-    while (clock64() < until) __nanosleep(1000);
-  }
-
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
   long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of the issuer: weights wait, MMA issue, MMA done, epilogue, barrier
   long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): expand, scan, backup, select, network
@@ -314,7 +299,6 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, FCfg<NT, WPT>::DUAL ? 
         }
         backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
                        SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH,
-                       AG_ROOT_SMEM ? SH.root + (lo >> 7) * SH.root_tile_stride + (lo & 127) * RootSlot<Lay::APAD>::BYTES : nullptr,
                        SH.nc_nodes > 0 ? SH.nc_base + (size_t)lo * SH.nc_nodes * RootSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
       }
       __syncthreads();

@@ -108,28 +108,10 @@ struct SearchParams {
 // of everything (the stores are off the critical path), so the stand-alone kernels and the read-back entry points see the same data.
 constexpr int PATH_SMEM_DEPTH = 16;          // path entries per game held in shared memory; deeper levels are read from global
 
-// Loads of the records ON A PATH (descent and backup).  Development variant -DAG_L2_HINT=1: they carry an L2 evict_last policy, so that
-// the lines of nodes which are visited again and again outlive those of leaves that never are (the live trees, 400 MB at the end of a
-// 32768-game ply, do not fit the 126 MB L2).  Default build: plain loads.
-#ifndef AG_L2_HINT
-#define AG_L2_HINT 0
-#endif
-#if AG_L2_HINT
-AG_D u64 l2_hot_policy() { u64 p; asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
-AG_D uint2 hot_ld_u2(const void* a) {
-  uint2 v; asm volatile("ld.global.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(a), "l"(l2_hot_policy()) : "memory"); return v;
-}
-AG_D uint4 hot_ld_u4(const void* a) {
-  uint4 v; asm volatile("ld.global.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(a), "l"(l2_hot_policy()) : "memory"); return v;
-}
-AG_D float4 hot_ld_f4(const void* a) {
-  float4 v; asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(a), "l"(l2_hot_policy()) : "memory"); return v;
-}
-#else
+// loads of the records on a path (descent and backup)
 AG_D uint2 hot_ld_u2(const void* a) { return *reinterpret_cast<const uint2*>(a); }
 AG_D uint4 hot_ld_u4(const void* a) { return *reinterpret_cast<const uint4*>(a); }
 AG_D float4 hot_ld_f4(const void* a) { return *reinterpret_cast<const float4*>(a); }
-#endif
 template <class G>
 struct RolloutShared {
   typename G::State* state;  // [GAMES] state of the leaf
@@ -140,19 +122,10 @@ struct RolloutShared {
   uint8_t* leaf;             // [GAMES]
   uint8_t* pn;               // [GAMES][PATH_SMEM_DEPTH] path nodes
   uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
-  unsigned char* root;       // AG_ROOT_SMEM: descent fields of the ROOT record (header, child ids, π̄), RootSlot<AP>::BYTES per game, left by the
-  int root_tile_stride;      //   backup item that re-solved the root; row gl at root + (gl / 128) * root_tile_stride + (gl % 128) * BYTES
   unsigned char* nc_base;    // AG_TREE_SMEM: write-through copy of the descent fields of the first nc_nodes nodes of every game of the CTA,
   int nc_nodes;              //   entry (gl, node) at nc_base + (gl * nc_nodes + node) * RootSlot<AP>::BYTES; 0 = no cache
 };
 
-// The root is on every path: each rollout's backup rewrites its π̄ and the next descent reads it back first thing — through L2, because the
-// writer is another thread (2 k cycles at 223 games per CTA, 0.6 k at 8).  The backup item of the root therefore also leaves the
-// descent's view of the record in shared memory.  Valid from the third rollout on: rollout 0 finds the root unexpanded (path length 0),
-// rollout 1 descends through it, so from rollout 2 on every backup phase has a root item.
-#ifndef AG_ROOT_SMEM
-#define AG_ROOT_SMEM 0
-#endif
 // -DAG_TREE_SMEM=<KB> (development variant, NOT YET RUN ON A GPU): the small-batch per-ply kernel spends <KB> of shared memory on a
 // write-through cache of the descent fields (header, child ids, π̄ — the RootSlot layout) of the first nodes of each of its games.  In
 // the tail of a generation a CTA holds <= 32 games and a rollout is a latency chain; a level of the descent is then a shared-memory read
@@ -179,9 +152,6 @@ AG_D void prefetch_l2(const void* a) {
   (void)a;
 #endif
 }
-#if AG_TREE_SMEM && AG_ROOT_SMEM
-#error "AG_TREE_SMEM subsumes AG_ROOT_SMEM: enable one of them"
-#endif
 template <int AP> struct RootSlot {
   static constexpr int OFF_CHILD = 8;                                  // after the 8-byte header
   static constexpr int OFF_POLICY = (8 + AP + 15) & ~15;
@@ -645,7 +615,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
 template <class G>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
-                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr, unsigned char* s_root = nullptr,
+                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr,
                       unsigned char* s_cache_row = nullptr, const int nc_nodes = 0) {
   const long long tr0 = tr ? clock64() : 0;
   typedef Layout<G> Lay;
@@ -691,12 +661,7 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
         for (int a = 0; a < A; a++) if (ch[a] != 0) prefetch_l2(gbase + (size_t)(ch[a] - 1) * REC);
 #endif
-#if AG_ROOT_SMEM
-        const uint2 hdr_w = hot_ld_u2(nrec + Lay::OFF_HDR);
-        const int nchild = (int)((hdr_w.x >> 16) & 0xFFu);
-#else
         const int nchild = reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR)->nchild;
-#endif
         // running mean of the child's value from this node's point of view (:319-320)
         float qold = 0.f; int vold = 0;
 #pragma unroll
@@ -730,21 +695,6 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
             for (int c = 0; c < AP / 4; c++)
               *reinterpret_cast<float4*>(s_cache_row + nd * RootSlot<AP>::BYTES + RootSlot<AP>::OFF_POLICY + 16 * c) =
                   make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
-          }
-#endif
-#if AG_ROOT_SMEM
-          if (s_root != nullptr && jj == 0) {                                        // the root: the next descent starts from this copy
-            *reinterpret_cast<uint2*>(s_root) = hdr_w;
-#pragma unroll
-            for (int c = 0; c < AP / 8; c++) {
-              uint32_t lo = 0, hi = 0;
-#pragma unroll
-              for (int e = 0; e < 4; e++) { lo |= (uint32_t)ch[8 * c + e] << (8 * e); hi |= (uint32_t)ch[8 * c + 4 + e] << (8 * e); }
-              *reinterpret_cast<uint2*>(s_root + RootSlot<AP>::OFF_CHILD + 8 * c) = make_uint2(lo, hi);
-            }
-#pragma unroll
-            for (int c = 0; c < AP / 4; c++)
-              *reinterpret_cast<float4*>(s_root + RootSlot<AP>::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
           }
 #endif
         }
@@ -781,14 +731,9 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
     u64 cw0, cw1 = 0;
     float pol[AP];
-#if AG_TREE_SMEM || AG_ROOT_SMEM
 #if AG_TREE_SMEM
     unsigned char* const csl = node_cache_slot<G>(SH, gl, node);                       // this node's cache entry, if it has one
     const unsigned char* sl = csl;
-#else
-    // the root as the backup phase of this rollout left it in shared memory (RootSlot)
-    const unsigned char* sl = (depth == 0 && rollout >= 2 && SH.root != nullptr) ? SH.root + (gl >> 7) * SH.root_tile_stride + (gl & 127) * RootSlot<AP>::BYTES : nullptr;
-#endif
     if (sl != nullptr) {
       hw = *reinterpret_cast<const uint2*>(sl);
       const uint2 cv = *reinterpret_cast<const uint2*>(sl + RootSlot<AP>::OFF_CHILD);

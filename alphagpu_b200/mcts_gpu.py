@@ -51,6 +51,7 @@ class Context:
     def __init__(self, spec: GameSpec, visits: int, ngames: int, width: int, blocks: int, device: int = 0, nn_mode: int = _lib.NN_FP16_TC):
         self.lib = _lib.load()
         self.spec, self.visits, self.ngames = spec, visits, ngames
+        self.width, self.blocks = width, blocks
         self.A, self.VS, self.FS = spec.maxActions, spec.VectorizedState, spec.FeatureSize
         cfg = _lib.Config(spec.game, spec.N, spec.Nvict, visits, ngames, width, blocks, device, nn_mode)
         h = C.c_void_p()
@@ -71,6 +72,14 @@ class Context:
 
     # ---- network ----
     def set_weights(self, net: SNetwork2, slot: int = 0):
+        # the C side trusts the shape the context was created with (width, blocks): a differently shaped actor would be read out of bounds
+        n, k, inp = self.width, self.blocks, 2 * self.VS
+        ok = (net.base.shape == (n, inp) and len(net.res) == k and all(r.shape == (n, n) for r in net.res) and net.policy.shape == (self.A, n)
+              and net.policy_bias.shape == (self.A,) and net.value.shape == (1, n) and net.value_bias.shape == (1,))
+        arrs = [net.base, *net.res, net.policy, net.policy_bias, net.value, net.value_bias]
+        ok = ok and all(a.dtype == np.float32 and (a.ndim < 2 or a.flags.f_contiguous) for a in arrs)
+        if not ok:
+            raise ValueError(f"set_weights: the actor does not match this context ({n}x{k}, {inp} inputs, {self.A} actions, float32 column-major)")
         arr = (C.c_void_p * max(1, net.blocks))(*[r.ctypes.data for r in net.res])
         check(self.h, self.lib.agpu_set_weights(self.h, slot, _p(net.base), C.cast(arr, C.c_void_p), _p(net.policy), _p(net.policy_bias),
                                                 _p(net.value), _p(net.value_bias)))
@@ -244,7 +253,33 @@ def _sum_over_ranks(values, device):
     return [int(v) for v in t.tolist()]
 
 
-def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample], *, spec: GameSpec, cpuct=2.0, noise=None, seed=0,
+def _fresh_seed(seed, device, backend):
+    """seed=None: fresh randomness on every call, as the reference's unseeded RNGs give (the Julia glue passes rand(UInt64)); drawn on
+    rank 0 and broadcast so that all ranks play one generation."""
+    if seed is not None:
+        return int(seed)
+    import secrets
+    seed = secrets.randbits(63)
+    rank, world, _ = _world()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([seed], dtype=torch.int64, device=f"cuda:{device}" if backend == "nccl" else None)
+        dist.broadcast(t, src=0)
+        seed = int(t.item())
+    return seed
+
+
+def _empty_run(spec: GameSpec):
+    """What a rank with no games contributes (ngames < world): zero counters and empty sample blocks, so it still joins the collectives."""
+    res = np.zeros(3, np.int64)
+    stats = {k: 0 for k, _ in _lib.RunStats._fields_}
+    out = dict(state=np.empty((0, 2 * spec.VectorizedState), np.int8), policy=np.empty((0, spec.maxActions), np.float32), player=np.empty(0, np.int8),
+               value=np.empty(0, np.float32), fstate=np.empty((0, spec.FeatureSize), np.int8), game=np.empty(0, np.int32), ply=np.empty(0, np.int32))
+    return res, stats, out
+
+
+def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample], *, spec: GameSpec, cpuct=2.0, noise=None, seed=None,
          uid_base=0, device=0, nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
     """mcts(actor, visits, ngames, buffer; cpuct, noise) (mcts_gpu.jl:477-579): one generation of self-play; samples are
     pushed into `buffer`.  Returns (data, valid) like the reference plus the run statistics.
@@ -259,13 +294,18 @@ def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample
         uid_base, ngames_local = uid_base + base, count
     else:
         ngames_local = ngames
+    seed = _fresh_seed(seed, device, backend)
     own = ctx is None
-    if own:
-        ctx = init(spec, visits, max(1, ngames_local), actor, device, nn_mode)
-    else:
-        ctx.set_weights(actor, 0)
     noise = float(2.0 / spec.maxActions) if noise is None else noise
-    res, stats, out = ctx.selfplay(visits, ngames_local, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
+    if ngames_local == 0:                                     # more ranks than games: nothing to play here, but the collectives below still run
+        own = False
+        res, stats, out = _empty_run(spec)
+    else:
+        if own:
+            ctx = init(spec, visits, ngames_local, actor, device, nn_mode)
+        else:
+            ctx.set_weights(actor, 0)
+        res, stats, out = ctx.selfplay(visits, ngames_local, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
     if world > 1:
         dev = f"cuda:{device}" if backend == "nccl" else None
         if buffer is not None:
@@ -282,7 +322,7 @@ def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample
     return dict(data=[], valid=stats["faults"] == 0, stats=stats)
 
 
-def mcts_duel(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, cpuct=2.0, seed=0, device=0,
+def mcts_duel(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, cpuct=2.0, seed=None, device=0,
               nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
     """mcts(actor1, actor2, visits, ngames; cpuct) (mcts_gpu.jl:581-651) -> [v, n, d].  Under torch.distributed the games are
     block-partitioned over the ranks and the three counts summed."""
@@ -291,21 +331,26 @@ def mcts_duel(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *,
     if world > 1:
         from .parallel import shard_games
         uid_base, ngames = shard_games(ngames, rank, world)
+    seed = _fresh_seed(seed, device, backend)
     own = ctx is None
-    if own:
-        ctx = Context(spec, visits, max(1, ngames), actor1.width, actor1.blocks, device, nn_mode)
-    ctx.set_weights(actor1, 0)
-    ctx.set_weights(actor2, 1)
-    res, _ = ctx.duel(visits, ngames, cpuct=cpuct, seed=seed, uid_base=uid_base)
-    if own:
-        ctx.close()
+    if ngames == 0:                                           # more ranks than games
+        res = np.zeros(3, np.int64)
+    else:
+        if own:
+            ctx = Context(spec, visits, ngames, actor1.width, actor1.blocks, device, nn_mode)
+        ctx.set_weights(actor1, 0)
+        ctx.set_weights(actor2, 1)
+        res, _ = ctx.duel(visits, ngames, cpuct=cpuct, seed=seed, uid_base=uid_base)
+        if own:
+            ctx.close()
     if world > 1:
         res = np.asarray(_sum_over_ranks(res, f"cuda:{device}" if backend == "nccl" else None), np.int64)
     return res
 
 
-def duelnetwork(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, seed=0, device=0, nn_mode=_lib.NN_FP16_TC):
+def duelnetwork(actor1: SNetwork2, actor2: SNetwork2, visits: int, ngames: int, *, spec: GameSpec, seed=None, device=0, nn_mode=_lib.NN_FP16_TC):
     """duelnetwork(actor1, actor2, visits, ngames) (mcts_gpu.jl:653-668): half the games with each net moving first."""
+    seed = _fresh_seed(seed, device, _world()[2])
     h = ngames // 2
     v1, n1, d1 = mcts_duel(actor1, actor2, visits, h, spec=spec, seed=seed, device=device, nn_mode=nn_mode)
     d2, n2, v2 = mcts_duel(actor2, actor1, visits, h, spec=spec, seed=seed + 1, device=device, nn_mode=nn_mode)

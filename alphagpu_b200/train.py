@@ -190,9 +190,8 @@ def traininPipe(batchsize: int, net: NetworkF, p, *, epoch: int = 1, lr: float =
     at cpt >= L, train.jl:81-84).  A fresh optimiser every call (train.jl:50).  Trains `net` in place (returns it) and reports
     (mean loss over the batches, seconds, samples/s of the last epoch).  Under torch.distributed every rank draws the same q
     (same seed) and trains on its `dp_slice` of each batch."""
-    import torch.distributed as dist
-    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
-    rank = dist.get_rank() if world > 1 else 0
+    from .mcts_gpu import _world
+    rank, world, _ = _world()                                   # (0, 1, None) without torch / outside a process group
     own = trainer is None
     per_rank = batchsize // world
     if own:

@@ -1155,7 +1155,7 @@ int orc_selfplay(int game, int N, int Nvict, void* netp, int visits, int64_t nga
       const float* pol = &t->policy_final[(size_t)s.A * i];
       float u = rng_uniform(seed, uids[i], round, ROLLOUT_MOVE, 0);
       int c = choose_move_selfplay(pol, s.A, round, u);
-      if (!can_play(s, positions[i], c)) { faults++; }                       // "faute" :526-529 (counted, not aborted: keeps the bench total defined)
+      if (!can_play(s, positions[i], c)) { faults++; }                       // "faute" :526-529 (counted; the loop stops after this ply)
       positions[i] = play(s, positions[i], c);
       int8_t res; bool f = is_over(s, positions[i], &res);
       if (f) {
@@ -1178,6 +1178,9 @@ int orc_selfplay(int game, int N, int Nvict, void* netp, int visits, int64_t nga
     }
     round++;
     L = (int64_t)positions.size();
+    // "faute" (:526-529): the reference returns valid=false at the first illegal move.  Restated per ply (the ply that produced it is
+    // completed, then the generation stops); the ply cap guards against positions an illegal move leaves unchanged.
+    if (faults > 0 || round > (uint32_t)s.maxLen + 8) break;
     if (L > 0) tree_reinit(t, positions.data(), uids.data(), L);             // :557-561
   }
   if (out) out->count = count;
@@ -1214,6 +1217,7 @@ int orc_duel(int game, int N, int Nvict, void* net1, void* net2, int visits, int
     for (size_t k = 0; k < finished.size(); k++) { int64_t c = finished[k] - (int64_t)k; positions.erase(positions.begin() + c); uids.erase(uids.begin() + c); }
     round++;
     L = (int64_t)positions.size();
+    if (faults > 0 || round > (uint32_t)s.maxLen + 8) break;                 // "faute" (:611-614)
     if (L > 0) tree_reinit(t, positions.data(), uids.data(), L);
   }
   results[0] = v; results[1] = n; results[2] = d;

@@ -1,7 +1,7 @@
 """Development: a library built with extra compile-time switches (python -m alphagpu_b200.build with AGPU_VARIANT / AGPU_EXTRA_NVCC)
 against the default library: identical self-play output (digest over every sample array) and device time per generation.
 
-    python scripts/lib_variant_experiment.py alphagpu_b200/libalphagpu_l2.so [--games 32768] [--reps 3]
+    python scripts/lib_variant_experiment.py alphagpu_b200/libalphagpu_a.so [alphagpu_b200/libalphagpu_b.so ...] [--games 32768] [--reps 3]
 
 AGPU_LIB is read when alphagpu_b200 is imported, so each library runs in its own process."""
 import argparse
@@ -39,12 +39,13 @@ print(json.dumps(out))
 """
 
 ap = argparse.ArgumentParser()
-ap.add_argument("lib")
+ap.add_argument("lib", nargs="+")
 ap.add_argument("--games", type=int, default=32768)
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 res = {}
-for name, lib in (("default", None), ("variant", os.path.abspath(a.lib)), ("default_again", None)):
+cases = [("default", None)] + [(os.path.basename(l).replace("libalphagpu_", "").replace(".so", ""), os.path.abspath(l)) for l in a.lib] + [("default_again", None)]
+for name, lib in cases:
     env = dict(os.environ)
     env.pop("AGPU_LIB", None)
     if lib:
@@ -54,7 +55,8 @@ for name, lib in (("default", None), ("variant", os.path.abspath(a.lib)), ("defa
         print(json.dumps(dict(case=name, error=p.stderr[-1500:])), flush=True)
         continue
     res[name] = json.loads(p.stdout.strip().splitlines()[-1])
-    print(json.dumps(dict(case=name, lib=lib, **res[name], best_ms=min(res[name]["ms"]))), flush=True)
-ok = "variant" in res and "default" in res and res["variant"]["digests"] == res["default"]["digests"]
-print(json.dumps(dict(identical_output=ok)))
+    same = res[name]["digests"] == res["default"]["digests"] if "default" in res else None
+    print(json.dumps(dict(case=name, lib=lib, identical_output=same, **res[name], best_ms=min(res[name]["ms"]))), flush=True)
+ok = all(r["digests"] == res["default"]["digests"] for r in res.values()) if "default" in res else False
+print(json.dumps(dict(all_identical=ok)))
 sys.exit(0 if ok else 1)
