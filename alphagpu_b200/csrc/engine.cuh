@@ -144,10 +144,7 @@ struct EngineT : EngineBase {
   // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
   static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;   // and width 128, checked at run time
   bool use_fused = false;
-  bool fused_swap = true;
-  int fused_wpt = 8;               // warps per tile of the two-tile variant: 8 = 512 threads x 128 registers (16: 1024 x 64, 91 vs 84 ms)
-  int fused_swap_max = 128;        // games per CTA up to which the 512-thread variant is launched
-  int num_sms = 148, fused_min_gpc = 8, fused_tiles = 2;   // 2 tiles per CTA measured faster than 1 tile x 2 CTAs per SM (117 vs 134 ms per generation)
+  int num_sms = 148, fused_min_gpc = 8;
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -255,18 +252,10 @@ struct EngineT : EngineBase {
     if (is_tc()) AG_CK(tc_init());
     if constexpr (FUSED_OK) {
       if (is_tc() && cfg.width == tc::TC_N) {
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
-        if (const char* e = getenv("AGPU_FUSED_TILES")) fused_tiles = atoi(e) == 2 ? 2 : 1;
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
         AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
-        if (const char* e = getenv("AGPU_FUSED_WPT")) fused_wpt = atoi(e) == 8 ? 8 : 16;
-        if (const char* e = getenv("AGPU_FUSED_SWAP")) fused_swap = atoi(e) != 0;
-        if (const char* e = getenv("AGPU_FUSED_SWAP_MAX")) fused_swap_max = atoi(e);
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
@@ -287,30 +276,23 @@ struct EngineT : EngineBase {
       T.img = (const unsigned char*)ns.dev.tc_img; T.bias = ns.dev.tc_bias; T.nlayers = ns.dev.k + 2; T.k0_steps = (ns.dev.in + 15) / 16;
       T.A = ns.dev.A; T.NH = tc::head_n(ns.dev.A); T.in = ns.dev.in; T.dbg = g_tc_dbg;
       SegParams S; S.off = 0; S.len = (int)L; S.ply = ply; S.training = training; S.seed = seed; S.cpuct = cpuct; S.pad = 0;
-      // games per CTA: spread the live games over all CTA slots of the chip (2 per SM with one tile per CTA), at least
-      // fused_min_gpc and at most 128 per tile
-      const int slots = num_sms * (fused_tiles == 1 ? 2 : 1), cap = 128 * fused_tiles;
-      int gpc = (int)((L + slots - 1) / slots);
+      // games per CTA: spread the live games over all SMs, at least fused_min_gpc and at most 256 (two 128-row tiles)
+      int gpc = (int)((L + num_sms - 1) / num_sms);
       gpc = (gpc + 7) / 8 * 8;
       if (gpc < fused_min_gpc) gpc = fused_min_gpc;
-      if (gpc > cap) gpc = cap;
+      if (gpc > 256) gpc = 256;
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (gpc <= fused_swap_max && fused_swap) {
-          // the tail of a generation: few games per CTA -> the 512-thread, 128-register, swapped-orientation variant
+        if (gpc <= 128) {
+          // the tail of a generation: at most one tile per CTA -> the 512-thread small-batch variant (16 warps on one tile; swapped
+          // orientation up to 64 games)
           if (fmt == 0) fused::ply_kernel<G, 0, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
-        } else if (fused_wpt == 8 && fused_tiles == 2) {
+        } else {
           // two tiles, 8 warps per tile: 512 threads with 128 registers each
           if (fmt == 0) fused::ply_kernel<G, 0, 2, false, 8><<<grid, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 2, false, 8><<<grid, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
-        } else if (fused_tiles == 1) {
-          if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
-        } else {
-          if (fmt == 0) fused::ply_kernel<G, 0, 2><<<grid, fused::FCfg<2>::THREADS, fused::FCfg<2>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 2><<<grid, fused::FCfg<2>::THREADS, fused::FCfg<2>::SMEM, stream>>>(P, T, S, visits, gpc);
         }
       });
       AG_CK(cudaGetLastError());

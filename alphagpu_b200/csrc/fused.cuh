@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
           int hi = C::GAMES;
           while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
         }
-        backup_item<G>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
+        backup_item<G, SW>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
                        SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH,
                        SH.nc_nodes > 0 ? SH.nc_base + (size_t)lo * SH.nc_nodes * RootSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
       }

@@ -230,9 +230,26 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
 // same order as the reference loop: sums ascending in the action, Newton terms in child-creation order starting from prior_rem/α.
 // vis = visits after the update; ord[k] = 1-based action of the k-th created child.
 // ------------------------------------------------------------------------------------------------
-template <int A, int AP>
+// v[idx] for a small register array without dynamic indexing (which would put the array in local memory): a binary tree of selects
+template <int AP> AG_D float sel_reg(const float (&v)[AP], const int idx) {
+  static_assert(AP == 8 || AP == 16, "select tree over 8 or 16 registers");
+  float t[AP / 2];
+#pragma unroll
+  for (int i = 0; i < AP / 2; i++) t[i] = (idx & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < AP / 4; i++) t[i] = (idx & 2) ? t[2 * i + 1] : t[2 * i];
+#pragma unroll
+  for (int i = 0; i < AP / 8; i++) t[i] = (idx & 4) ? t[2 * i + 1] : t[2 * i];
+  if (AP == 16) return (idx & 8) ? t[1] : t[0];
+  return t[0];
+}
+
+// SPEC (the small-batch kernel, where a rollout is a latency chain): the quotients of the derivative are issued together with those of
+// the sum instead of after the convergence test — one batch of independent divisions per iteration instead of two dependent ones.  The
+// derivative of the last iteration is computed and dropped, as the reference does (:144-151 computes both in the same loop).
+template <int A, int AP, bool SPEC = false>
 AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis)[AP], const int (&ch)[AP], const int (&ord)[AP],
-                     const int nchild, const float cpuct, float (&pol)[AP], const char* q_rec, const char* prior_rec, long long* tr = nullptr) {
+                     const int nchild, const float cpuct, float (&pol)[AP], long long* tr = nullptr) {
   int nv = 0, acount = 0;
   float rem = 0.f;
 #pragma unroll
@@ -245,18 +262,20 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
   const float lambda = fdiv(fmul(cpuct, fsqrt(n)), fadd((float)acount, n));      // :132
   rem = fmul(rem, lambda);                                                          // :134
   float alpha = 0.f;
+  float top[AP];
 #pragma unroll
-  for (int a = 0; a < A; a++) alpha = fmaxf(alpha, fadd(q[a], fmaxf(fmul(lambda, p[a]), 1e-4f)));   // :135-138
-  // statistics of the children in slot (creation) order, gathered from the record by address — the caller has already stored
-  // the updated q there — instead of 2*A*A register selects
+  for (int a = 0; a < AP; a++) top[a] = a < A ? fmul(lambda, p[a]) : 0.f;
+#pragma unroll
+  for (int a = 0; a < A; a++) alpha = fmaxf(alpha, fadd(q[a], fmaxf(top[a], 1e-4f)));   // :135-138
+  // statistics of the children in slot (creation) order — the order of the Newton sums — picked out of the registers
   float tops[AP], qs[AP];
 #pragma unroll
   for (int k = 0; k < A; k++) {
     tops[k] = 0.f; qs[k] = 0.f;
     if (k < nchild) {
       const int a = ord[k] - 1;
-      qs[k] = *reinterpret_cast<const float*>(q_rec + 4 * a);
-      tops[k] = fmul(lambda, *reinterpret_cast<const float*>(prior_rec + 4 * a));
+      qs[k] = sel_reg<AP>(q, a);
+      tops[k] = sel_reg<AP>(top, a);
     }
   }
   // Fast-division plan (common.cuh: fdiv_fast): every numerator below is loop-invariant and non-negative, every denominator positive.
@@ -274,17 +293,28 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
 #pragma unroll
     for (int k = 0; k < A; k++) { bot[k] = fsub(alpha, qs[k]); bmin = fminf(bmin, bot[k]); bmax = fmaxf(bmax, bot[k]); }
     const bool fast = num_ok && bmin >= SQ_LO && bmax <= SQ_HI;                      // (a NaN denominator fails the comparison chain below)
-    float S;
+    float S, G = 0.f;
     if (fast) {
       // all quotients first — independent, branch-free, staged so that they overlap in the pipeline — then the adds in reference order
-      float na[A + 1], nb[A + 1], nq[A + 1];
+      constexpr int NQ = SPEC ? 2 * (A + 1) : A + 1;
+      float na[NQ], nb[NQ], nq[NQ];
       na[0] = rem; nb[0] = alpha;
 #pragma unroll
       for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = bot[k]; }
-      fdiv_fast_n<A + 1>(na, nb, nq);
+      if (SPEC) {
+        na[A + 1] = rem; nb[A + 1] = fmul(alpha, alpha);
+#pragma unroll
+        for (int k = 0; k < A; k++) { na[A + 2 + k] = tops[k]; nb[A + 2 + k] = fmul(bot[k], bot[k]); }
+      }
+      fdiv_fast_n<NQ>(na, nb, nq);
       S = nq[0];
 #pragma unroll
       for (int k = 0; k < A; k++) if (k < nchild) S = fadd(S, nq[k + 1]);
+      if (SPEC) {
+        G = nq[A + 1];
+#pragma unroll
+        for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[A + 2 + k]);
+      }
     } else {
       S = fdiv(rem, alpha);
 #pragma unroll
@@ -294,14 +324,16 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
     if (newerr < 0.001f || newerr == err) break;
     // the derivative is only needed when the iteration continues (the reference computes it in the same loop and drops it on exit)
     if (fast && alpha == alpha) {
-      float na[A + 1], nb[A + 1], nq[A + 1];
-      na[0] = rem; nb[0] = fmul(alpha, alpha);
+      if (!SPEC) {
+        float na[A + 1], nb[A + 1], nq[A + 1];
+        na[0] = rem; nb[0] = fmul(alpha, alpha);
 #pragma unroll
-      for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = fmul(bot[k], bot[k]); }
-      fdiv_fast_n<A + 1>(na, nb, nq);
-      float G = nq[0];
+        for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = fmul(bot[k], bot[k]); }
+        fdiv_fast_n<A + 1>(na, nb, nq);
+        G = nq[0];
 #pragma unroll
-      for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[k + 1]);
+        for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[k + 1]);
+      }
       alpha = fadd(alpha, fdiv(newerr, G));
     } else {
       float gs = fdiv(-rem, fmul(alpha, alpha));
@@ -313,21 +345,11 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
   }
   if (tr) tr[3] += clock64() + (__float_as_int(alpha) & 0) - trs;
   {
-    // π̄_a = λ p_a / (α - q_a) (:165-169).  p and q are read again from the record (first-level cache) rather than kept in registers
-    // across the Newton loop: at the kernel's 64-register cap the loop needs them for overlapping its divisions.
+    // π̄_a = λ p_a / (α - q_a) (:165-169)
     float num[A], den[A];
     bool ok = true;
 #pragma unroll
-    for (int c = 0; c < AP / 4; c++) {
-      float pv[4], qv[4];
-      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(pv[0]), "=f"(pv[1]), "=f"(pv[2]), "=f"(pv[3]) : "l"(prior_rec + 16 * c) : "memory");
-      asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(qv[0]), "=f"(qv[1]), "=f"(qv[2]), "=f"(qv[3]) : "l"(q_rec + 16 * c) : "memory");
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int a = 4 * c + e;
-        if (a < A) { num[a] = fmul(lambda, pv[e]); den[a] = fsub(alpha, qv[e]); ok = ok && fdiv_box_den(den[a]) && fdiv_box_num(num[a]); }
-      }
-    }
+    for (int a = 0; a < A; a++) { num[a] = top[a]; den[a] = fsub(alpha, q[a]); ok = ok && fdiv_box_den(den[a]) && fdiv_box_num(num[a]); }
     if (ok) {
       float nq[A];
       fdiv_fast_n<A>(num, den, nq);
@@ -613,7 +635,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // jj = index in the recorded path (0 = root), d = path length.  Each ancestor is a different node, so items are independent;
 // the value an ancestor receives is the leaf value flipped once per level below it (value = 1 - value, :324), evaluated as that
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
-template <class G>
+template <class G, bool SPEC = false>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
                       long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr,
                       unsigned char* s_cache_row = nullptr, const int nc_nodes = 0) {
@@ -684,7 +706,7 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
         long long tr1 = 0;
         if (tr) { tr1 = clock64() + (__float_as_int(qnew) & 0); tr[0] += tr1 - tr0; }
         if (!last_rollout) {
-          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol, nrec + Lay::OFF_Q, nrec + Lay::OFF_PRIOR, tr);
+          solve_node<A, AP, SPEC>(p, q, vis, ch, ord, nchild, cpuct, pol, tr);
           if (tr) { tr[1] += clock64() + (__float_as_int(pol[0]) & 0) - tr1; tr[2] += 1; }
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
@@ -724,6 +746,10 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   uint8_t* pnode = P.path_node + (size_t)g * P.R;
   uint8_t* pmove = P.path_move + (size_t)g * P.R;
   uint2 hw;
+  // The state of the node the descent stands on is carried in registers: read once for the root (together with the loads of level 0)
+  // and advanced with play() at every step — a child's stored state IS play(parent state, action), so the value is the same — instead
+  // of one more dependent round trip for the parent's state when the leaf is created.
+  typename G::State cur = *reinterpret_cast<const typename G::State*>(gbase + Lay::OFF_STATE);
 
   while (true) {
     char* rec = gbase + (size_t)node * REC;
@@ -787,7 +813,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     if (tr && depth == 0) trA = clock64() + (hw.x & 0) + (__float_as_int(pol[A - 1]) & 0) + ((u32)cw0 & 0);
     if (!(flags & F_EXPANDED)) {                                                      // while expanded[nindex]==1  (:110)
       // an existing node that is not expanded: the root before its first evaluation, or a terminal node
-      SH.state[gl] = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+      SH.state[gl] = cur;
       SH.hdr[gl] = *reinterpret_cast<const NodeHdr*>(&hw);
       break;
     }
@@ -821,8 +847,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
       *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
       *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
       reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
-      const typename G::State ps = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
-      const typename G::State ns = G::play(ps, best + 1);
+      const typename G::State ns = G::play(cur, best + 1);
       int res = 0;
       const bool term = G::is_over(ns, res);
       char* nrec = gbase + (size_t)(c - 1) * REC;
@@ -856,6 +881,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     }
     node = c - 1;                                                                      // :192
     depth += 1;
+    cur = G::play(cur, best + 1);
     if (tr && depth == 1) trD = clock64() + (node & 0);
   }
   if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }

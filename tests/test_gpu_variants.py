@@ -21,4 +21,4 @@ def test_variant_library_reproduces_the_default_output(lib):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "lib_variant_experiment.py"), lib, "--games", "8192", "--reps", "1"],
                          capture_output=True, text=True, timeout=600)
     last = json.loads(out.stdout.strip().splitlines()[-1])
-    assert out.returncode == 0 and last == {"identical_output": True}, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.returncode == 0 and last == {"all_identical": True}, out.stdout[-2000:] + out.stderr[-2000:]
