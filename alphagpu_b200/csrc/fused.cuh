@@ -70,40 +70,31 @@ AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[8]) { tmem_st8(taddr, v);
 AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
 
 // Epilogue of a trunk layer computed in the SWAPPED orientation (few games per CTA): the accumulator holds out-feature f in TMEM
-// lane f and game n in column n.  This thread owns feature 32*wq + lane and the NC games of slice cs; it applies relu / the
-// residual, keeps the fp32 stream in TMEM (same transposed shape) and scatters the 16-bit operand of the next layer into the
-// ordinary games x features, K-major, 128B-swizzled tile (so the head layer and the encoder need no second layout).
-// -DAG_SWAP_RESREG=1 (development variant, NOT YET RUN ON A GPU): in the swapped orientation a thread owns the same NC (8 or 16) residual
-// values in every layer, so they can stay in registers (sres) instead of making a TMEM round trip per layer (tcgen05.ld + st + wait::st).
-#ifndef AG_SWAP_RESREG
-#define AG_SWAP_RESREG 0
+// lane f and game n in column n.  This thread owns feature 32*wq + lane and the NC games of slice cs in every layer, so the fp32
+// residual stream stays in its registers (sres); it applies relu / the residual and scatters the 16-bit operand of the next layer into
+// the ordinary games x features, K-major, 128B-swizzled tile (so the head layer and the encoder need no second layout).
+// KS accumulator chains (AG_KSPLIT): the layer's 8 K-steps are dealt round-robin to KS accumulators, NS columns apart, so that
+// consecutive tcgen05.mma instructions do not wait on each other's accumulator; the partial sums are added here, pairwise.
+#ifndef AG_KSPLIT
+#define AG_KSPLIT 1
 #endif
-template <int FMT, int NC>
-AG_D void epilogue_swapped(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs, int lane, int l, bool keep, unsigned char* At, uint32_t (&sres)[16]) {
-  uint32_t va[NC], vh[NC];
+template <int FMT, int NC, int KS>
+AG_D void epilogue_swapped(uint32_t tmem_acc, int NS, int wq, int cs, int lane, int l, unsigned char* At, uint32_t (&sres)[16]) {
+  static_assert(KS == 1 || KS == 2 || KS == 4, "accumulator chains");
+  uint32_t va[KS][NC], vh[NC];
   const uint32_t taddr = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * NC);
-  tmem_ldn(tmem_acc + taddr, va);
-#if AG_SWAP_RESREG
-  (void)tmem_res; (void)keep;
+#pragma unroll
+  for (int c = 0; c < KS; c++) tmem_ldn(tmem_acc + taddr + (uint32_t)(c * NS), va[c]);
   tmem_ld_wait();
 #pragma unroll
   for (int e = 0; e < NC; e++) {
-    const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
+    float acc = __uint_as_float(va[0][e]);
+    if (KS == 2) acc = acc + __uint_as_float(va[1][e]);
+    if (KS == 4) acc = (acc + __uint_as_float(va[1][e])) + (__uint_as_float(va[2][e]) + __uint_as_float(va[3][e]));
+    const float ra = fmaxf(acc, 0.f);
     const float hv = (l == 0) ? ra : __uint_as_float(sres[e]) + ra;
     sres[e] = vh[e] = __float_as_uint(hv);
   }
-#else
-  (void)sres;
-  if (l > 0) tmem_ldn(tmem_res + taddr, vh);
-  tmem_ld_wait();
-#pragma unroll
-  for (int e = 0; e < NC; e++) {
-    const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
-    const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
-    vh[e] = __float_as_uint(hv);
-  }
-  if (keep) tmem_stn(tmem_res + taddr, vh);
-#endif
   const int f = 32 * wq + lane;
   unsigned char* base = At + (f >> 6) * TC_KTILE_BYTES_A + (f & 7) * 2;
   const int c = (f & 63) >> 3;
@@ -241,6 +232,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   const int my_g = S.off + cta_first + (int)threadIdx.x;
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
+  typename G::State my_root = G::init();                               // the root's state: constant for the whole ply
+  if (has_game) my_root = *reinterpret_cast<const typename G::State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
+  // Philox block (depths 0..3) of the NEXT descent, computed while this thread would otherwise wait for the first MMA of a network phase
+  Philox4 rnd_next = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
   if (threadIdx.x < C::GAMES) s_d[threadIdx.x] = 0;
 #if AG_TREE_SMEM
   // fill the node cache with the nodes that exist when the ply starts (the root alone after root_reset); read back only by this thread
@@ -305,7 +300,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // (d) descent of this rollout
-    if (has_game) select_game1<G>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
+    if (has_game) select_game1<G>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, my_root, rnd_next, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
     __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
@@ -339,7 +334,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
     fence_proxy_async();
     named_bar_sync(1 + t, 32 * WPT);
 
-    uint32_t sres[16];                                                 // AG_SWAP_RESREG: this thread's residual values (swapped orientation)
+    uint32_t sres[16];                                                 // this thread's residual values (swapped orientation)
     for (int l = 0; l < nlayers; l++, wl++) {
       const int s = wl % STAGES;
       const bool is_head = (l == nlayers - 1);
@@ -362,7 +357,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
             for (int ks = 0; ks < TC_N / 16; ks++) {
               const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
               const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-              umma_bf16(tmem_acc_u, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
+              umma_bf16(tmem_acc_u + (uint32_t)((ks % AG_KSPLIT) * NS), bd0 + binc, ad0 + ainc, idesc, ks >= AG_KSPLIT ? 1u : 0u);   // weights as A, activations as B
             }
           }
 #if AG_NHALF
@@ -409,6 +404,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
       // the weights two layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the issuer
       // the request sat on the critical path: 2 k cycles per rollout)
       if (warp == 1 && lane == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
+      if (l == 0 && has_game) rnd_next = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
       mbar_wait(bar_done + 8 * t, wl & 1);
 #if AG_NHALF
       const bool split = NHALF && !is_head && !(SW && swapped);         // CTA-uniform: this layer was issued as two column halves
@@ -419,12 +415,10 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
       if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
 
       if (SW && swapped && !is_head) {
-        const bool keep = (l + 2 < nlayers);
         if constexpr (SW) {
-          if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At, sres);
-          else epilogue_swapped<FMT, 16>(tmem_acc, tmem_res, wq, csb, lane, l, keep, At, sres);
+          if (NS == 32) epilogue_swapped<FMT, 8, AG_KSPLIT>(tmem_acc, NS, wq, csb, lane, l, At, sres);
+          else epilogue_swapped<FMT, 16, AG_KSPLIT>(tmem_acc, NS, wq, csb, lane, l, At, sres);
         }
-        tmem_st_wait();
         tc_fence_before();
         fence_proxy_async();
         long long lt4 = 0;
@@ -540,7 +534,7 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
                 if (a0 + 4 * q4 < Lay::OUTS) {
                   const float4 zv = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
                   *reinterpret_cast<float4*>(so + a0 + 4 * q4) = zv;
-                  *reinterpret_cast<float4*>(o + a0 + 4 * q4) = zv;
+                  if (last) *reinterpret_cast<float4*>(o + a0 + 4 * q4) = zv;     // the expand of the last rollout reads it from global memory
                 }
             }
           }

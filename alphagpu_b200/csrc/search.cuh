@@ -23,7 +23,7 @@ namespace ag {
 
 enum : uint8_t { F_EXPANDED = 1, F_TERMINAL = 2 };
 
-struct NodeHdr {
+struct alignas(8) NodeHdr {
   uint8_t parent;   // 1-based node id, 0 = root has none            (vnodes.parent)
   uint8_t action;   // 1-based action from parent                    (vnodes.actionFromParent)
   uint8_t nchild;   //                                               (vnodesStats.childnbr)
@@ -32,6 +32,13 @@ struct NodeHdr {
   uint8_t pad[3];
 };
 static_assert(sizeof(NodeHdr) == 8, "header");
+// a header as ONE 8-byte word: field-by-field assignment through a pointer compiles to eight byte stores, i.e. eight requests to the
+// memory pipeline per new node (ncu, round 1: 8 of the 129 L1 requests of a simulation)
+AG_HD u64 hdr_word(int parent, int action, int nchild, int flags, int result) {
+  return (u64)(uint8_t)parent | ((u64)(uint8_t)action << 8) | ((u64)(uint8_t)nchild << 16) | ((u64)(uint8_t)flags << 24) | ((u64)(uint8_t)(int8_t)result << 32);
+}
+AG_D void hdr_store(void* p, u64 w) { *reinterpret_cast<u64*>(p) = w; }
+AG_D NodeHdr hdr_from_word(u64 w) { NodeHdr h; *reinterpret_cast<u64*>(&h) = w; return h; }
 
 constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
@@ -204,6 +211,21 @@ template <int APL, class T> AG_D T pick(const T (&v)[APL], int j) {
   return r;
 }
 
+// a State as 8-byte words (one or a few wide stores instead of a store per field)
+template <class S> AG_D void state_store(void* dst, const S& st) {
+  static_assert(sizeof(S) % 8 == 0, "state size");
+  union { S s; u64 w[sizeof(S) / 8]; } u;
+  u.w[sizeof(S) / 8 - 1] = 0;
+  u.s = st;
+  if constexpr (sizeof(S) == 24) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4((u32)u.w[0], (u32)(u.w[0] >> 32), (u32)u.w[1], (u32)(u.w[1] >> 32));
+    *reinterpret_cast<u64*>(reinterpret_cast<char*>(dst) + 16) = u.w[2];
+  } else {
+#pragma unroll
+    for (int i = 0; i < (int)(sizeof(S) / 8); i++) reinterpret_cast<u64*>(dst)[i] = u.w[i];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // root install: re_init (mcts_gpu.jl:359-373) + the fills of mcts_single (:380-387) for node 1 only.
 // src == null keeps the stored root state (agpu_search_begin).
@@ -219,8 +241,7 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
   if (uid) P.uid[g] = uid[g];
   // zero the statistics (prior, q, visits, child, order, π̄)
   for (int o = Lay::STATS_BEGIN; o < Lay::STATS_END; o += 8) *reinterpret_cast<uint2*>(rec + o) = make_uint2(0, 0);
-  NodeHdr h; h.parent = 0; h.action = 0; h.nchild = 0; h.flags = 0; h.result = 0; h.pad[0] = h.pad[1] = h.pad[2] = 0;
-  *reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR) = h;
+  hdr_store(rec + Lay::OFF_HDR, 0ull);
   P.nnodes[g] = 1;
   P.leaf[g] = 0;
 }
@@ -520,9 +541,7 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
         *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + h.nchild) = (uint8_t)(best + 1);
         reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(h.nchild + 1);
         *reinterpret_cast<typename G::State*>(nrec + Lay::OFF_STATE) = ns;
-        NodeHdr nh; nh.parent = (uint8_t)(node + 1); nh.action = (uint8_t)(best + 1); nh.nchild = 0;
-        nh.flags = term ? F_TERMINAL : 0; nh.result = (int8_t)res; nh.pad[0] = nh.pad[1] = nh.pad[2] = 0;
-        *reinterpret_cast<NodeHdr*>(nrec + Lay::OFF_HDR) = nh;
+        hdr_store(nrec + Lay::OFF_HDR, hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res));
       }
       node = c - 1;
       depth += 1;
@@ -732,24 +751,29 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 // per game issues an eighth of the instructions; the seven-term prefix scan it serialises is shorter than the shuffles it replaces.
 // Same operations in the same order as select_game / expand_game: results are bit-identical.
 // ------------------------------------------------------------------------------------------------
+// root: the root's state, held in a register by the game's thread for the whole ply.  rnd0: the Philox block of depths 0..3 of THIS rollout,
+// computed ahead of time (under the network phase of the previous rollout) so that it is off the descent's critical path.
+// The copies in global memory of what the descent hands to the next phases (leaf, node count, path) are written on the last rollout of a
+// ply — that is when the stand-alone kernels and the read-back entry points look at them — and for path entries beyond the shared-memory
+// window; during the loop they travel through shared memory only (a third of the descent's requests to the memory pipeline were these).
 template <class G>
 AG_D void select_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, const u32 uid, int& nn, int rollout, int last_rollout,
-                       u64 seed, u32 ply, long long* tr = nullptr) {
+                       u64 seed, u32 ply, const typename G::State& root, const Philox4& rnd0, long long* tr = nullptr) {
   const long long tr0 = tr ? clock64() : 0;
   long long trA = tr0, trB = tr0, trC = tr0, trD = tr0;
   typedef Layout<G> Lay;
   static_assert(Lay::FAST, "thread-per-game descent needs the stored policy");
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
   char* gbase = P.tree + (size_t)g * P.game_stride;
-  int node = 0, depth = 0, rblock = -1;
-  Philox4 rnd; rnd.v[0] = rnd.v[1] = rnd.v[2] = rnd.v[3] = 0;
+  int node = 0, depth = 0, rblock = 0;
+  Philox4 rnd = rnd0;
   uint8_t* pnode = P.path_node + (size_t)g * P.R;
   uint8_t* pmove = P.path_move + (size_t)g * P.R;
   uint2 hw;
-  // The state of the node the descent stands on is carried in registers: read once for the root (together with the loads of level 0)
-  // and advanced with play() at every step — a child's stored state IS play(parent state, action), so the value is the same — instead
-  // of one more dependent round trip for the parent's state when the leaf is created.
-  typename G::State cur = *reinterpret_cast<const typename G::State*>(gbase + Lay::OFF_STATE);
+  // The state of the node the descent stands on is carried in registers and advanced with play() at every step — a child's stored
+  // state IS play(parent state, action), so the value is the same — instead of one more dependent round trip for the parent's state
+  // when the leaf is created.
+  typename G::State cur = root;
 
   while (true) {
     char* rec = gbase + (size_t)node * REC;
@@ -814,7 +838,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     if (!(flags & F_EXPANDED)) {                                                      // while expanded[nindex]==1  (:110)
       // an existing node that is not expanded: the root before its first evaluation, or a terminal node
       SH.state[gl] = cur;
-      SH.hdr[gl] = *reinterpret_cast<const NodeHdr*>(&hw);
+      *reinterpret_cast<uint2*>(&SH.hdr[gl]) = hw;
       break;
     }
     if (node == 0 && last_rollout) {                                                  // copy_pol (:330-339)
@@ -837,8 +861,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     }
     if (best < 0) best = 0;
     if (tr && depth == 0) trC = clock64() + (best & 0);
-    pnode[depth] = (uint8_t)node;
-    pmove[depth] = (uint8_t)best;
+    if (last_rollout || depth >= PATH_SMEM_DEPTH) { pnode[depth] = (uint8_t)node; pmove[depth] = (uint8_t)best; }
     if (depth < PATH_SMEM_DEPTH) { SH.pn[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)node; SH.pm[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)best; }
     int c = (int)(((AP == 16 && best >= 8 ? cw1 : cw0) >> (8 * (best & 7))) & 0xFFu);
     if (c == 0) {                                                                     // allocate the child (:183-191)
@@ -858,23 +881,22 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
         *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
       }
-      *reinterpret_cast<typename G::State*>(nrec + Lay::OFF_STATE) = ns;
-      NodeHdr nh; nh.parent = (uint8_t)(node + 1); nh.action = (uint8_t)(best + 1); nh.nchild = 0;
-      nh.flags = term ? F_TERMINAL : 0; nh.result = (int8_t)res; nh.pad[0] = nh.pad[1] = nh.pad[2] = 0;
-      *reinterpret_cast<NodeHdr*>(nrec + Lay::OFF_HDR) = nh;
+      state_store(nrec + Lay::OFF_STATE, ns);
+      const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
+      hdr_store(nrec + Lay::OFF_HDR, nhw);
 #if AG_TREE_SMEM
       if (csl != nullptr) {                                                            // the parent's entry: child id and child count
         csl[RootSlot<AP>::OFF_CHILD + best] = (uint8_t)c;
         csl[2] = (uint8_t)(nchild + 1);                                                // NodeHdr::nchild
       }
       if (unsigned char* nsl = node_cache_slot<G>(SH, gl, c - 1)) {                    // the new node's entry (π̄ is written by expand)
-        *reinterpret_cast<NodeHdr*>(nsl) = nh;
+        hdr_store(nsl, nhw);
 #pragma unroll
         for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint2*>(nsl + RootSlot<AP>::OFF_CHILD + 8 * k) = make_uint2(0, 0);
       }
 #endif
       SH.state[gl] = ns;
-      SH.hdr[gl] = nh;
+      hdr_store(&SH.hdr[gl], nhw);
       node = c - 1;
       depth += 1;
       break;
@@ -887,9 +909,11 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }
   SH.leaf[gl] = (uint8_t)node;
   SH.d[gl] = depth;
-  P.leaf[g] = node;                                                                    // :195
-  P.nnodes[g] = nn;
-  P.path_len[g] = (uint8_t)depth;
+  if (last_rollout) {
+    P.leaf[g] = node;                                                                  // :195
+    P.nnodes[g] = nn;
+    P.path_len[g] = (uint8_t)depth;
+  }
   if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)depth); atomicAdd(&P.counters[1], 1ull); }
 }
 
