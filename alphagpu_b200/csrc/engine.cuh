@@ -252,10 +252,10 @@ struct EngineT : EngineBase {
     if (is_tc()) AG_CK(tc_init());
     if constexpr (FUSED_OK) {
       if (is_tc() && cfg.width == tc::TC_N) {
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<1>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<2, 8>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 2>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 2>::SMEM));
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
@@ -285,14 +285,13 @@ struct EngineT : EngineBase {
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
         if (gpc <= 128) {
-          // the tail of a generation: at most one tile per CTA -> the 512-thread small-batch variant (16 warps on one tile; swapped
-          // orientation up to 64 games)
-          if (fmt == 0) fused::ply_kernel<G, 0, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 1, true><<<grid, fused::FCfg<1>::THREADS, fused::FCfg<1>::SMEM, stream>>>(P, T, S, visits, gpc);
+          // the tail of a generation: at most one tile per CTA -> the small-batch kernel (swapped orientation up to 64 games, node cache)
+          if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
         } else {
-          // two tiles, 8 warps per tile: 512 threads with 128 registers each
-          if (fmt == 0) fused::ply_kernel<G, 0, 2, false, 8><<<grid, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 2, false, 8><<<grid, fused::FCfg<2, 8>::THREADS, fused::FCfg<2, 8>::SMEM, stream>>>(P, T, S, visits, gpc);
+          // two 128-row tiles per CTA, served alternately by all 16 warps
+          if (fmt == 0) fused::ply_kernel<G, 0, 2><<<grid, fused::FCfg<G, 2>::THREADS, fused::FCfg<G, 2>::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 2><<<grid, fused::FCfg<G, 2>::THREADS, fused::FCfg<G, 2>::SMEM, stream>>>(P, T, S, visits, gpc);
         }
       });
       AG_CK(cudaGetLastError());

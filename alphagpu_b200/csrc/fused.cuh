@@ -1,15 +1,17 @@
 // fused.cuh — one persistent kernel per ply: the whole R-rollout loop of mcts_single (mcts_gpu.jl:396-439) on chip.
 //
-// A CTA owns 256 games (two 128-row tiles) for the entire search of a ply and alternates, per rollout,
-//   search phase : all 1024 threads, 8 lanes per game, two passes of 128 games: expand+backUp of the previous rollout, then the
-//                  descent of this one (the same device functions as the stand-alone kernels, search.cuh);
-//   network phase: the tcgen05/TMEM chain of nn_tc.cu re-organised for 32 warps: warp w serves tile w/16, TMEM lane quarter w%4
-//                  and the 32-column slice (w/4)%4; one lane per tile issues the MMAs; the fp32 residual stream lives in TMEM
-//                  (columns 256..511) so the epilogue needs few registers; weights stream global->shared through the 3-stage
-//                  bulk-copy ring without ever draining between rollouts.
-// Games of a CTA depend on each other only through their shared GEMM tile, so there is no grid-wide barrier and no kernel
-// boundary inside a ply: the per-rollout cost is the on-chip critical path instead of three launches plus their tails
-// (profiles/r01_ply_trace_*.txt: 70 us -> per rollout at 32768 games, 25-40 us floor at small L with separate launches).
+// A CTA of 512 threads (16 warps x 128 registers) owns up to 256 games for the entire search of a ply and alternates, per rollout,
+//   search phase : ONE POOL of warp-sized work units drawn from a shared-memory counter — the (game, ancestor) items of backUp + the
+//                  α re-solve (search.cuh: backup_item), listed level by level by the descents that produced them, and the expansion of
+//                  the leaves (expand_game1), 32 games per unit — then, behind one barrier, the descent of the next rollout, one thread
+//                  per game (select_game1).  Everything a phase hands to the next lives in shared memory (RolloutShared).
+//   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves.  All 16 warps serve one 128-row tile at a time — TMEM
+//                  lane quarter w%4, 32-column slice w/4 — and with two tiles (129..256 games) they ALTERNATE: the epilogue of tile 0
+//                  runs under the MMAs of tile 1 and vice versa, so the tensor pipe and the epilogue warps are both busy.  The fp32
+//                  residual stream lives in TMEM (ordinary orientation) or in registers (swapped orientation); weights stream
+//                  global -> shared through a bulk-copy ring that never drains between rollouts.
+// Games of a CTA depend on each other only through their shared GEMM tile, so there is no grid-wide barrier and no kernel boundary
+// inside a ply: the per-rollout cost is the on-chip critical path instead of three launches plus their tails.
 #pragma once
 #include "search.cuh"
 #include "tc_ptx.cuh"
@@ -19,31 +21,19 @@ namespace ag {
 namespace fused {
 using namespace tc;
 
-// -DAG_NHALF=1 (development variant, NOT YET RUN ON A GPU): with 8 warps per tile a trunk layer in the ordinary orientation is issued as
-// two chains of 8 MMAs, output columns 0..63 and 64..127 (two barriers), and every warp owns one 32-column slice in EACH half: it runs
-// the TMEM loads, the arithmetic and the residual store of its first slice while the tensor core still works on the second half; the
-// operands computed from the first slice are stored only once that second chain — which reads the same tile as its A operand — is done.
-// Every column is accumulated over K in the same order as before, so the results are bit-identical.
-#ifndef AG_NHALF
-#define AG_NHALF 0
-#endif
-
-// NT = tiles per CTA.  NT = 2: 1024 threads, one CTA per SM, 3-stage weight ring.  NT = 1: 512 threads, 2-stage ring, TWO CTAs per
-// SM (98 KB shared memory, 256 TMEM columns, 64 registers each): while one CTA waits on its MMA chain the other's search phase
-// uses the issue slots.
-template <int NT, int WPT = 16> struct FCfg {
-  static constexpr int THREADS = 32 * WPT * NT;                        // WPT warps per tile: 16 (one 32-column slice per warp) or 8 (two)
+// NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
+// the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
+// cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
+template <class G, int NT> struct FCfg {
+  static constexpr int THREADS = 512;
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  static constexpr int ITEM_MAP = 1024;                                // backup items whose game is looked up in a byte map
-  static constexpr int WORK = 2048 + GAMES * (44 + 72); // barriers/bias/backup work list + rollout hand-off
-  static constexpr int WORK_USED = 640 + GAMES * 32 + GAMES * 4 + (GAMES + 1) * 4 + 16 + GAMES * 68 + ITEM_MAP;   // as laid out in the kernel
-  static_assert(WORK_USED <= WORK, "shared-memory work area overflows its budget");
-  // AG_TREE_SMEM (KB): node cache of the one-tile, 16-warp kernels (the small-batch variant of the tail), after the work area
-  static constexpr int TREE_BYTES = (NT == 1 && WPT == 16) ? AG_TREE_SMEM * 1024 : 0;
+  static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * BACKUP_LEVELS + 1 + 2 * PATH_SMEM_DEPTH;
+  static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
+  static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
   static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
-  static constexpr int CTAS_PER_SM = NT == 1 ? 2 : 1;
+  static_assert(SMEM <= 227 * 1024, "shared memory per CTA");
 };
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -59,41 +49,24 @@ AG_D void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
-AG_D void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
-               : "memory");
-}
 AG_D void tmem_ldn(uint32_t taddr, uint32_t (&v)[8]) { tmem_ld8(taddr, v); }
 AG_D void tmem_ldn(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
-AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[8]) { tmem_st8(taddr, v); }
-AG_D void tmem_stn(uint32_t taddr, const uint32_t (&v)[16]) { tmem_st16(taddr, v); }
 
 // Epilogue of a trunk layer computed in the SWAPPED orientation (few games per CTA): the accumulator holds out-feature f in TMEM
 // lane f and game n in column n.  This thread owns feature 32*wq + lane and the NC games of slice cs in every layer, so the fp32
 // residual stream stays in its registers (sres); it applies relu / the residual and scatters the 16-bit operand of the next layer into
 // the ordinary games x features, K-major, 128B-swizzled tile (so the head layer and the encoder need no second layout).
-// KS accumulator chains (AG_KSPLIT): the layer's 8 K-steps are dealt round-robin to KS accumulators, NS columns apart, so that
-// consecutive tcgen05.mma instructions do not wait on each other's accumulator; the partial sums are added here, pairwise.
-#ifndef AG_KSPLIT
-#define AG_KSPLIT 1
-#endif
-template <int FMT, int NC, int KS>
-AG_D void epilogue_swapped(uint32_t tmem_acc, int NS, int wq, int cs, int lane, int l, unsigned char* At, uint32_t (&sres)[16]) {
-  static_assert(KS == 1 || KS == 2 || KS == 4, "accumulator chains");
-  uint32_t va[KS][NC], vh[NC];
+template <int FMT, int NC>
+AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, int l, unsigned char* At, uint32_t (&sres)[16]) {
+  uint32_t va[NC];
   const uint32_t taddr = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * NC);
-#pragma unroll
-  for (int c = 0; c < KS; c++) tmem_ldn(tmem_acc + taddr + (uint32_t)(c * NS), va[c]);
+  tmem_ldn(tmem_acc + taddr, va);
   tmem_ld_wait();
 #pragma unroll
   for (int e = 0; e < NC; e++) {
-    float acc = __uint_as_float(va[0][e]);
-    if (KS == 2) acc = acc + __uint_as_float(va[1][e]);
-    if (KS == 4) acc = (acc + __uint_as_float(va[1][e])) + (__uint_as_float(va[2][e]) + __uint_as_float(va[3][e]));
-    const float ra = fmaxf(acc, 0.f);
+    const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
     const float hv = (l == 0) ? ra : __uint_as_float(sres[e]) + ra;
-    sres[e] = vh[e] = __float_as_uint(hv);
+    sres[e] = __float_as_uint(hv);
   }
   const int f = 32 * wq + lane;
   unsigned char* base = At + (f >> 6) * TC_KTILE_BYTES_A + (f & 7) * 2;
@@ -101,85 +74,108 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, int NS, int wq, int cs, int lane, 
 #pragma unroll
   for (int e = 0; e < NC; e++) {
     const int n = cs * NC + e;
-    *reinterpret_cast<uint16_t*>(base + n * 128 + ((c ^ (n & 7)) << 4)) = (uint16_t)(pack2<FMT>(__uint_as_float(vh[e]), 0.f) & 0xFFFFu);
+    *reinterpret_cast<uint16_t*>(base + n * 128 + ((c ^ (n & 7)) << 4)) = (uint16_t)(pack2<FMT>(__uint_as_float(sres[e]), 0.f) & 0xFFFFu);
   }
 }
 
+// Epilogue of a trunk layer in the ordinary orientation: row r = 32*wq + lane of the tile, the 32 columns of slice cs.
+// b = relu(acc) (base layer) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b).
+template <int FMT>
+AG_D void epilogue_ordinary(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs, int lane, int l, bool keep, unsigned char* At) {
+  const int r = wq * 32 + lane;
+  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    uint32_t va[16], vh[16];
+    tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
+    if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
+    tmem_ld_wait();
+#pragma unroll
+    for (int e = 0; e < 16; e++) {
+      const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
+      const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
+      vh[e] = __float_as_uint(hv);
+    }
+    if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh);
+#pragma unroll
+    for (int c2 = 0; c2 < 2; c2++) {
+      const int c = 4 * cs + 2 * i + c2;
+      const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[8 * c2 + 0]), __uint_as_float(vh[8 * c2 + 1])),
+                                  pack2<FMT>(__uint_as_float(vh[8 * c2 + 2]), __uint_as_float(vh[8 * c2 + 3])),
+                                  pack2<FMT>(__uint_as_float(vh[8 * c2 + 4]), __uint_as_float(vh[8 * c2 + 5])),
+                                  pack2<FMT>(__uint_as_float(vh[8 * c2 + 6]), __uint_as_float(vh[8 * c2 + 7])));
+      *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
+    }
+  }
+  tmem_st_wait();
+}
 
-// SW: the small-batch variant (host: games per CTA <= 128): one tile, 512 threads, one CTA per SM — 128 registers per thread instead
-// of 64 — and, up to 64 games, the trunk layers in the swapped orientation (below).
-template <class G, int FMT, int NT, bool SW = false, int WPT = 16>
-__global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 : FCfg<NT, WPT>::CTAS_PER_SM) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
-  static_assert(!SW || (NT == 1 && WPT == 16), "the swapped variant runs a single tile with 16 warps");
-  static_assert(WPT == 16 || WPT == 8, "warps per tile");
+template <class G, int FMT, int NT>
+__global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   typedef Layout<G> Lay;
-  typedef FCfg<NT, WPT> C;
-  constexpr int CPW = 16 / WPT;                                        // 32-column slices per warp
+  typedef FCfg<G, NT> C;
+  typedef typename G::State State;
+  constexpr bool SMALL = NT == 1;                                      // the small-batch kernel: swapped orientation, node cache
   constexpr int W = Lay::W;
   constexpr int STAGES = C::STAGES;
   static_assert(Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= TC_N, "fused ply kernel: small boards only");
-  // gpc = games per CTA (<= 256), chosen by the host so that the live games spread over all SMs: the search phase of a CTA is
-  // issue-bound on its one SM, so late plies run many lightly filled CTAs rather than a few full ones.
+  static_assert(C::GAMES <= 256, "items carry the local game in 8 bits");
+  // gpc = games per CTA (<= 256), chosen by the host so that the live games spread over all SMs: late plies run many lightly filled
+  // CTAs rather than a few full ones.
   const int cta_first = (int)blockIdx.x * gpc;                         // first local slot of this CTA
   if (cta_first >= S.len) return;
   const int count = min(gpc, S.len - cta_first);                       // games of this CTA
-  const int L_end = S.off + cta_first + count;                         // one past this CTA's last slot
+  const int g0 = S.off + cta_first;                                    // global slot of local game 0
   const int ntiles = (NT == 2 && count > TC_TILE_M) ? 2 : 1;           // a CTA with <= 128 games runs a single tile
   // Few games per CTA (the long tail of a generation): the trunk layers run as D^T = W * X^T — out-features on the M = 128 side, the
   // NS = 32 / 64 games on the N side — so the tensor time and the epilogue shrink with the batch instead of paying for 128 rows.
   // The weight image (out x in, K-major) serves as the A operand unchanged and the activation tile as the B operand unchanged.
-  const bool swapped = SW && count <= 64;                              // CTA-uniform; 65..128 games keep the ordinary orientation
+  const bool swapped = SMALL && count <= 64;                           // CTA-uniform; 65..128 games keep the ordinary orientation
   const int NS = count <= 32 ? 32 : 64;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  unsigned char* sA = smem;                                            // [2][32 KB] activations (A operands)
+  unsigned char* sA = smem;                                            // [NT][32 KB] activations (A operands)
   unsigned char* sW = smem + NT * TC_A_BYTES;                          // [STAGES][32 KB] weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * TC_W_STAGE_BYTES);
-  // bars[0..2] full, [3..5] empty, [6..7] mma_done, [8] stagger (one-shot)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  float* sbias = reinterpret_cast<float*>(bars + 10);                  // [128] head biases
-  // work list of the backup phase: per game of the CTA the leaf evaluation, the path length and its exclusive prefix sum
-  LeafEval* s_eval = reinterpret_cast<LeafEval*>(bars + 80);           // [256]
-  int* s_d = reinterpret_cast<int*>(s_eval + C::GAMES);                // [256]
-  int* s_off = s_d + C::GAMES;                                         // [257]
-  // hand-off between the phases of a rollout (search.cuh: RolloutShared), 128 bytes per game
+  // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  int* s_next = reinterpret_cast<int*>(bars + 17);                     // [2] work-unit counters of the search pool, by rollout parity
+  int* s_lvcnt = reinterpret_cast<int*>(bars + 18);                    // [2][BACKUP_LEVELS] items per level, by rollout parity
+  float* sbias = reinterpret_cast<float*>(bars + 18) + 2 * BACKUP_LEVELS;   // [128] head biases
+  static_assert(18 * 8 + 2 * BACKUP_LEVELS * 4 + TC_N * 4 <= 1024, "fixed part of the work area");
+  // hand-off between the phases of a rollout (search.cuh: RolloutShared)
   RolloutShared<G> SH;
-  SH.state = reinterpret_cast<typename G::State*>((reinterpret_cast<uintptr_t>(s_off + C::GAMES + 1) + 15) & ~uintptr_t(15));   // 16-byte aligned (float4 reads of `out`)
-  SH.hdr = reinterpret_cast<NodeHdr*>(SH.state + C::GAMES);
-  SH.d = s_d;
-  SH.leaf = reinterpret_cast<uint8_t*>(SH.hdr + C::GAMES);
+  SH.state = reinterpret_cast<State*>(reinterpret_cast<unsigned char*>(bars) + 1024);      // 16-byte aligned
+  SH.root = SH.state + C::GAMES;
+  SH.rnd = reinterpret_cast<Philox4*>(SH.root + C::GAMES);
+  SH.hdr = reinterpret_cast<NodeHdr*>(SH.rnd + C::GAMES);
+  SH.d = reinterpret_cast<int*>(SH.hdr + C::GAMES);
+  SH.lv_item = reinterpret_cast<uint16_t*>(SH.d + C::GAMES);
+  SH.lv_stride = C::GAMES;
+  SH.lv_cnt = s_lvcnt;
+  SH.leaf = reinterpret_cast<uint8_t*>(SH.lv_item + BACKUP_LEVELS * C::GAMES);
   SH.pn = SH.leaf + C::GAMES;
   SH.pm = SH.pn + C::GAMES * PATH_SMEM_DEPTH;
-  constexpr int ITEM_MAP = C::ITEM_MAP;                                // backup items whose game is looked up in a byte map (the rest: binary search)
-  static_assert(sizeof(LeafEval) == 32 && sizeof(NodeHdr) == 8, "FCfg::WORK_USED assumes these sizes");
-  uint8_t* s_item = SH.pm + C::GAMES * PATH_SMEM_DEPTH;                // [ITEM_MAP] item -> local game
+  static_assert(sizeof(State) % 8 == 0 && sizeof(Philox4) == 16 && sizeof(NodeHdr) == 8, "hand-off layout");
   // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
-  // expand reads the outputs in between.  (Staying under 196 KB of shared memory keeps the next carve-out step — 32 KB of L1 — free.)
+  // the search phase reads the outputs in between
   SH.out = reinterpret_cast<float*>(sA);
   SH.out_tile_stride = TC_A_BYTES / 4;
-  // node cache (AG_TREE_SMEM): the first nc_nodes nodes of each of this CTA's games; the fewer games, the deeper the cache
-  SH.nc_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sW + STAGES * TC_W_STAGE_BYTES + C::WORK) + 15) & ~uintptr_t(15));
-  SH.nc_nodes = C::TREE_BYTES > 0 ? min(P.R, (C::TREE_BYTES - 16) / (RootSlot<Lay::APAD>::BYTES * count)) : 0;
   static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_A_BYTES, "the network's outputs live in the idle A tile");
-  static_assert(sizeof(typename G::State) + 8 + 1 + 2 * PATH_SMEM_DEPTH <= 68, "rollout hand-off budget per game");
-  static_assert(FCfg<2>::SMEM <= 195 * 1024, "shared memory beyond the 196 KB carve-out costs 32 KB of L1");
+  // node cache (small-batch kernel): the first nc_nodes nodes of each of this CTA's games; the fewer games, the deeper the cache
+  SH.nc_base = reinterpret_cast<unsigned char*>(bars) + C::WORK;
+  SH.nc_nodes = SMALL ? min(P.R, C::TREE_BYTES / (CacheSlot<Lay::APAD>::BYTES * count)) : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
-#if AG_NHALF
-  constexpr bool NHALF = CPW == 2;                                     // only where a warp owns a slice in each column half
-  const uint32_t bar_done2 = smem_u32(bars + 74);                      // [2] all MMAs of the layer (the 48 bytes behind sbias are free)
-#endif
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, ntiles); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
     for (int t = 0; t < NT; t++) mbar_init(bar_done + 8 * t, 1);
-#if AG_NHALF
-    if (NHALF) for (int t = 0; t < NT; t++) mbar_init(bar_done2 + 8 * t, 1);
-#endif
-    mbar_init(bar_stagger, 1);
     fence_barrier_init();
+    s_next[0] = s_next[1] = 0;
+    for (int i = 0; i < 2 * BACKUP_LEVELS; i++) s_lvcnt[i] = 0;
   }
   if (threadIdx.x < TC_N) sbias[threadIdx.x] = T.bias[threadIdx.x];
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);        // NT x 128 accumulator columns + NT x 128 residual columns
@@ -190,134 +186,157 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
 
   const int nlayers = T.nlayers;
   const int total_layers = visits * nlayers;
-  // weight image of global layer index wl (= rollout * nlayers + layer) -> ring stage wl % 3
+  // weight image of global layer index wl (= rollout * nlayers + layer) -> ring stage wl % STAGES
   auto load_layer = [&](int wl) {
     const int s = wl % STAGES, l = wl % nlayers;
     const uint32_t bytes = (l == nlayers - 1) ? (uint32_t)(T.NH * TC_N * 2) : (uint32_t)TC_W_STAGE_BYTES;
-    if (NT == 2 && wl >= STAGES) mbar_wait(bar_empty + 8 * s, ((wl / STAGES) - 1) & 1);
+    if (wl >= STAGES) mbar_wait(bar_empty + 8 * s, ((wl / STAGES) - 1) & 1);
     mbar_expect_tx(bar_full + 8 * s, bytes);
     bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + (size_t)l * TC_W_STAGE_BYTES, bytes, bar_full + 8 * s);
   };
-  if (threadIdx.x == 0) {                                              // fill the ring: STAGES - 1 layers ahead
-    load_layer(0);
-    if (STAGES > 2 && total_layers > 1) load_layer(1);
+  if (threadIdx.x == 32) {                                             // fill the ring: STAGES - 1 layers ahead
+    for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
   }
 
   // ---- roles ----
-  // search: group of W lanes per game, pass p covers local games p*128 .. p*128+127
-  const int sg = threadIdx.x / W, sl = threadIdx.x & (W - 1);
-  const unsigned gm = group_mask<W>();
-  constexpr int GROUPS = C::THREADS / W;                               // games per pass
-  constexpr int PASSES = C::GAMES / GROUPS;
-  // network: tile, TMEM lane quarter, 32-column slice
-  const int t = warp / WPT, wq = warp & 3, csb = ((warp >> 2) & (WPT / 4 - 1)) * CPW;   // first column slice of this warp
+  // network: TMEM lane quarter and 32-column slice of this warp; its thread carries row r of whichever tile is being served
+  const int wq = warp & 3, cs = warp >> 2;
   const int r = wq * 32 + lane;
-  const int g_row = S.off + cta_first + t * TC_TILE_M + r;            // the game whose activations this thread carries
-  unsigned char* At = sA + t * TC_A_BYTES;
-  const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
-  const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
-  const uint32_t lane_row = (uint32_t)(wq * 32) << 16;
-  // The MMA-issuing warp of a tile takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived
-  // from values the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent
-  // `lane == 0` branch each MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
+  // The MMA-issuing warp takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived from values
+  // the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent `lane == 0` branch each
+  // MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const int t_u = warp_u / WPT;
-  const bool issuer_warp = (warp_u % WPT) == 0;
-  const uint32_t tmem_acc_u = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(t_u * TC_N);
-  const uint32_t a_smem_u = smem_u32(sA) + (uint32_t)(t_u * TC_A_BYTES);
+  const bool issuer_warp = warp_u == 0;
+  const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
-  // one thread per game for the descent and the expansion: its uid and node count stay in registers for the whole ply
+  // one thread per game for the descent: the game's uid and node count stay in its registers for the whole ply; the root's state and the
+  // first Philox block of the coming descent wait in shared memory
   const bool has_game = (int)threadIdx.x < count;
-  const int my_g = S.off + cta_first + (int)threadIdx.x;
+  const int my_g = g0 + (int)threadIdx.x;
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
-  typename G::State my_root = G::init();                               // the root's state: constant for the whole ply
-  if (has_game) my_root = *reinterpret_cast<const typename G::State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
-  // Philox block (depths 0..3) of the NEXT descent, computed while this thread would otherwise wait for the first MMA of a network phase
-  Philox4 rnd_next = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
-  if (threadIdx.x < C::GAMES) s_d[threadIdx.x] = 0;
-#if AG_TREE_SMEM
-  // fill the node cache with the nodes that exist when the ply starts (the root alone after root_reset); read back only by this thread
   if (has_game) {
-    const char* gb = P.tree + (size_t)my_g * P.game_stride;
-    for (int nd = 0; nd < min(my_nn, SH.nc_nodes); nd++) {
-      unsigned char* sl = node_cache_slot<G>(SH, (int)threadIdx.x, nd);
-      const char* rec = gb + (size_t)nd * Lay::REC;
-      *reinterpret_cast<uint2*>(sl) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
-      for (int c = 0; c < Lay::APAD / 8; c++) *reinterpret_cast<uint2*>(sl + RootSlot<Lay::APAD>::OFF_CHILD + 8 * c) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8 * c);
-      for (int c = 0; c < Lay::APAD / 4; c++) *reinterpret_cast<float4*>(sl + RootSlot<Lay::APAD>::OFF_POLICY + 16 * c) = *reinterpret_cast<const float4*>(rec + Lay::OFF_POLICY + 16 * c);
+    SH.root[threadIdx.x] = *reinterpret_cast<const State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
+    SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
+    SH.d[threadIdx.x] = 0;
+    if (SMALL) {
+      // fill the node cache with the nodes that exist when the ply starts (the root alone after root_reset); read back only by this thread
+      typedef CacheSlot<Lay::APAD> CS;
+      const char* gb = P.tree + (size_t)my_g * P.game_stride;
+      for (int nd = 0; nd < min(my_nn, SH.nc_nodes); nd++) {
+        unsigned char* sl = node_cache_slot<G, true>(SH, (int)threadIdx.x, nd);
+        const char* rec = gb + (size_t)nd * Lay::REC;
+        *reinterpret_cast<uint2*>(sl) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
+        for (int c = 0; c < Lay::APAD / 8; c++) *reinterpret_cast<uint2*>(sl + CS::OFF_CHILD + 8 * c) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8 * c);
+        for (int c = 0; c < Lay::APAD / 4; c++) *reinterpret_cast<float4*>(sl + CS::OFF_POLICY + 16 * c) = *reinterpret_cast<const float4*>(rec + Lay::OFF_POLICY + 16 * c);
+      }
     }
   }
-#endif
+  __syncthreads();
+
+  // issue of one layer's MMAs for tile t (called by the issuer warp only, all lanes, warp-uniform arguments)
+  auto issue_layer = [&](const int t, const int l, const int wl_) {
+    const int s = wl_ % STAGES;
+    const bool is_head = (l == nlayers - 1);
+    const int nl = is_head ? T.NH : TC_N;
+    tc_fence_after();
+    if (elect_one()) {
+      const uint32_t tmem_acc_u = tmem_base_u + (uint32_t)(t * TC_N);
+      const uint64_t ad0 = umma_desc(smem_u32(sA) + (uint32_t)(t * TC_A_BYTES));
+      const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * TC_W_STAGE_BYTES));
+      const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
+      if (SMALL && swapped && !is_head) {
+        const uint32_t idesc = umma_idesc<FMT>(NS);                     // M = 128 out-features, N = NS games
+#pragma unroll
+        for (int ks = 0; ks < TC_N / 16; ks++) {
+          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+          umma_bf16(tmem_acc_u, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
+        }
+      } else {
+        const uint32_t idesc = umma_idesc<FMT>(nl);
+#pragma unroll
+        for (int ks = 0; ks < TC_N / 16; ks++) {
+          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+          umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+        }
+      }
+      umma_commit(bar_done + 8 * t);
+      if (t == ntiles - 1) umma_commit(bar_empty + 8 * s);              // the stage is free once the last tile's MMAs of this layer are done
+    }
+    __syncwarp();
+  };
 
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
-  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of the issuer: weights wait, MMA issue, MMA done, epilogue, barrier
-  long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): expand, scan, backup, select, network
+  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: weights wait, MMA issue, MMA done, epilogue, barrier
+  long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): -, -, search pool, descent, network
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
     // ================= search phase =================
     if (k > 0) {
-      // (a) expand every game of the CTA (softmax, legal mask, prior), one thread per game, leaving the leaf evaluation in shared memory;
-      // (b) meanwhile the last warp — never a game thread at these sizes — prefix-sums the path lengths of the previous descent and
-      //     fills the item -> game map of the backup phase
-      if (has_game) s_eval[threadIdx.x] = expand_game1<G>(P, my_g, (int)threadIdx.x, SH, S.training, 0);
-      if (warp == C::THREADS / 32 - 1) {
-        constexpr int PER = C::GAMES / 32;
-        int loc[PER], dd[PER], sum = 0;
-#pragma unroll
-        for (int i = 0; i < PER; i++) { dd[i] = s_d[lane * PER + i]; loc[i] = sum; sum += dd[i]; }
-        int incl = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
-        const int excl = incl - sum;
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
-          const int off = excl + loc[i];
-          s_off[lane * PER + i] = off;
-          for (int j = 0; j < dd[i]; j++) if (off + j < ITEM_MAP) s_item[off + j] = (uint8_t)(lane * PER + i);
-        }
-        if (lane == 31) s_off[C::GAMES] = incl;
+      // The pool: backup items first (the longer units), then the expansions.  The items were listed, level by level, by the descents of
+      // rollout k-1 (SH.lv_item); a unit is 32 consecutive items or the leaves of 32 consecutive games.  A (game, ancestor) item and the
+      // expansion of that game's leaf touch different nodes, and both only read what the network and the descent left in shared memory,
+      // so the units are independent.
+      const int par = (k - 1) & 1;
+      const int* cnt = s_lvcnt + par * BACKUP_LEVELS;
+      if (threadIdx.x == 0) {                                          // counters of the other parity: for the coming descent / the next pool
+        s_next[par ^ 1] = 0;
+        for (int lv = 0; lv < BACKUP_LEVELS; lv++) s_lvcnt[(par ^ 1) * BACKUP_LEVELS + lv] = 0;
       }
-      __syncthreads();
-      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[0] += c - t_mark; t_mark = c; }
-      // (c) backUp + re-solve of π̄: one (game, ancestor) item per THREAD, packed densely over the CTA — with a lane group per
-      //     game only d of its 8 lanes (46 % on average) had an ancestor to work on, and the solve is 40 % of the search time
-      const int items = s_off[C::GAMES];
-      for (int i = threadIdx.x; i < items; i += C::THREADS) {
-        int lo = 0;
-        if (i < ITEM_MAP) {
-          lo = s_item[i];
-        } else {                                                       // largest gl with s_off[gl] <= i
-          int hi = C::GAMES;
-          while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (s_off[mid] <= i) lo = mid; else hi = mid; }
+      int n_items = 0;
+#pragma unroll
+      for (int lv = 0; lv < BACKUP_LEVELS; lv++) n_items += cnt[lv];
+      const int UB = (n_items + 31) >> 5, UE = (count + 31) >> 5;
+      while (true) {
+        int u = 0;
+        if (lane == 0) u = atomicAdd(&s_next[par], 1);
+        u = __shfl_sync(0xffffffffu, u, 0);
+        if (u >= UB + UE) break;
+        if (u < UB) {
+          // backUp + re-solve of π̄: one (game, ancestor) item per thread
+          const int i = u * 32 + lane;
+          if (i < n_items) {
+            int lv = 0, base = 0;
+            while (lv < BACKUP_LEVELS - 1 && i >= base + cnt[lv]) { base += cnt[lv]; lv++; }
+            const int item = SH.lv_item[lv * C::GAMES + (i - base)];
+            const int gl = item & 0xFF, jj = item >> 8;
+            const LeafEval E = leaf_eval1<G>(SH, gl);
+            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
+                           SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
+                           SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
+          }
+        } else {
+          const int gl = (u - UB) * 32 + lane;
+          if (gl < count) expand_game1<G, SMALL>(P, g0 + gl, gl, SH, S.training, 0);
         }
-        backup_item<G, SW>(P, S.off + cta_first + lo, i - s_off[lo], s_d[lo], s_eval[lo], 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
-                       SH.pn + lo * PATH_SMEM_DEPTH, SH.pm + lo * PATH_SMEM_DEPTH,
-                       SH.nc_nodes > 0 ? SH.nc_base + (size_t)lo * SH.nc_nodes * RootSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
       }
       __syncthreads();
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
-    // (d) descent of this rollout
-    if (has_game) select_game1<G>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, my_root, rnd_next, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
-    __syncthreads();                                                   // leaves (global) visible to the encoders of this CTA
+    // descent of this rollout; its path nodes are listed as the items of the next pool (parity k)
+    SH.lv_cnt = s_lvcnt + (k & 1) * BACKUP_LEVELS;
+    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
+    __syncthreads();
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
-    {
-      // A operand of the base layer: this thread's 32 operand columns of its row (decoder, mcts_gpu.jl:202-223)
-      u64 x0 = 0, x1 = 0;
-      if (g_row < L_end) {
-        const u64* st = reinterpret_cast<const u64*>(SH.state + t * TC_TILE_M + r);     // left there by this rollout's descent
-        const u64 bp = st[0], bo = st[1];
-        constexpr int VS = G::VS;
-        x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
-        x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
-      }
+    // A operand of the base layer (decoder, mcts_gpu.jl:202-223): this thread's 32 operand columns of its row, for each tile
 #pragma unroll
-      for (int j = 0; j < CPW; j++) {
-        const int cs = csb + j;
+    for (int t = 0; t < NT; t++) {
+      if (t < ntiles) {
+        u64 x0 = 0, x1 = 0;
+        const int gl = t * TC_TILE_M + r;
+        if (gl < count) {
+          const u64* st = reinterpret_cast<const u64*>(SH.state + gl);    // left there by this rollout's descent
+          const u64 bp = st[0], bo = st[1];
+          constexpr int VS = G::VS;
+          x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
+          x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
+        }
+        unsigned char* At = sA + t * TC_A_BYTES;
         const uint32_t bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -330,219 +349,95 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
         }
       }
     }
-    if (t >= ntiles) { wl += nlayers; __syncthreads(); continue; }      // idle tile: rejoin at the end-of-rollout barrier
     fence_proxy_async();
-    named_bar_sync(1 + t, 32 * WPT);
+    __syncthreads();
+    // base layer of every tile
+    {
+      long long lt0 = 0;
+      const bool ltr = T.dbg != nullptr && threadIdx.x == 0;
+      if (ltr) lt0 = clock64();
+      if (issuer_warp) {
+        mbar_wait(bar_full + 8 * (wl % STAGES), (wl / STAGES) & 1);
+        for (int t = 0; t < ntiles; t++) issue_layer(t, 0, wl);
+      }
+      if (ltr) t_ly[1] += clock64() - lt0;
+    }
+    // the weights STAGES - 1 layers ahead are requested by a lane that would otherwise just wait for MMAs
+    if (threadIdx.x == 32 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
+    // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run
+    if (has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
 
     uint32_t sres[16];                                                 // this thread's residual values (swapped orientation)
     for (int l = 0; l < nlayers; l++, wl++) {
-      const int s = wl % STAGES;
       const bool is_head = (l == nlayers - 1);
-      const int nl = is_head ? T.NH : TC_N;
-      long long lt0 = 0, lt1 = 0, lt2 = 0;
       const bool ltr = T.dbg != nullptr && threadIdx.x == 0 && !is_head;
-      if (ltr) lt0 = clock64();
-      if (issuer_warp) {
-        mbar_wait(bar_full + 8 * s, (wl / STAGES) & 1);
-        if (ltr) lt1 = clock64();
-        if (wl == 0 && t_u == 1) mbar_wait(bar_stagger, 0);            // tile 1 trails tile 0 by one MMA phase
+      for (int t = 0; t < ntiles; t++) {
+        unsigned char* At = sA + t * TC_A_BYTES;
+        const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
+        const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
+        long long lt2 = 0, lt3 = 0, lt4 = 0;
+        if (ltr && t == 0) lt2 = clock64();
+        mbar_wait(bar_done + 8 * t, wl & 1);
         tc_fence_after();
-        if (elect_one()) {
-          const uint64_t ad0 = umma_desc(a_smem_u);
-          const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * TC_W_STAGE_BYTES));
-          const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
-          if (SW && swapped && !is_head) {
-            const uint32_t idesc = umma_idesc<FMT>(NS);                 // M = 128 out-features, N = NS games
+        if (ltr && t == 0) { lt3 = clock64(); t_ly[2] += lt3 - lt2; }
+        if (!is_head) {
+          if (SMALL && swapped) {
+            if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, cs, lane, l, At, sres);
+            else epilogue_swapped<FMT, 16>(tmem_acc, wq, cs, lane, l, At, sres);
+          } else {
+            epilogue_ordinary<FMT>(tmem_acc, tmem_res, wq, cs, lane, l, l + 2 < nlayers, At);   // the last trunk layer's residual is not read again
+          }
+          tc_fence_before();
+          fence_proxy_async();
+          if (ltr && t == 0) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
+          __syncthreads();                                             // every warp has written its part of the next A operand of tile t
+          if (ltr && t == 0) t_ly[4] += clock64() - lt4;
+          // next layer of tile t: its MMAs run under the epilogue of the other tile
+          if (issuer_warp) {
+            long long lt0 = 0, lt1 = 0;
+            if (ltr && t == 0) lt0 = clock64();
+            if (t == 0) mbar_wait(bar_full + 8 * ((wl + 1) % STAGES), ((wl + 1) / STAGES) & 1);
+            if (ltr && t == 0) { lt1 = clock64(); t_ly[0] += lt1 - lt0; }
+            issue_layer(t, l + 1, wl + 1);
+            if (ltr && t == 0) t_ly[1] += clock64() - lt1;
+          }
+          if (t == ntiles - 1 && threadIdx.x == 32 && wl + STAGES < total_layers) load_layer(wl + STAGES);
+        } else {
+          // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> shared memory (read by the next search phase)
+          const int gl = t * TC_TILE_M + r;
+          const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
 #pragma unroll
-            for (int ks = 0; ks < TC_N / 16; ks++) {
-              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-              umma_bf16(tmem_acc_u + (uint32_t)((ks % AG_KSPLIT) * NS), bd0 + binc, ad0 + ainc, idesc, ks >= AG_KSPLIT ? 1u : 0u);   // weights as A, activations as B
+          for (int i = 0; i < 2; i++) {
+            const int a0 = cs * 32 + i * 16;
+            if (a0 < T.NH) {                                            // warp-uniform
+              uint32_t v[16];
+              tmem_ld16(tmem_acc + lane_sel + 16 * i, v);
+              tmem_ld_wait();
+              float z[16];
+#pragma unroll
+              for (int e = 0; e < 16; e++) z[e] = __uint_as_float(v[e]) + sbias[a0 + e];
+              if (T.A >= a0 && T.A < a0 + 16) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) if (a0 + e == T.A) z[e] = c_sigmoidf(z[e]);
+              }
+              if (gl < count) {
+                float* so = SH.out + t * SH.out_tile_stride + r * Lay::OUTS;
+                float* o = P.nn_out + (size_t)(g0 + gl) * Lay::OUTS;
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++)
+                  if (a0 + 4 * q4 < Lay::OUTS) {
+                    const float4 zv = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
+                    *reinterpret_cast<float4*>(so + a0 + 4 * q4) = zv;
+                    if (last) *reinterpret_cast<float4*>(o + a0 + 4 * q4) = zv;   // the expand of the last rollout reads it from global memory
+                  }
+              }
             }
           }
-#if AG_NHALF
-          else if (NHALF && !is_head) {
-            const uint32_t idesc = umma_idesc<FMT>(TC_N / 2);           // 64 output columns per chain
-#pragma unroll
-            for (int ks = 0; ks < TC_N / 16; ks++) {
-              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-              umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
-            }
-            umma_commit(bar_done + 8 * t_u);                             // columns 0..63 are complete
-            const uint64_t brow = (uint64_t)(((TC_N / 2) * 128) >> 4);   // weight rows 64..127: 8 swizzle atoms further in each K tile
-#pragma unroll
-            for (int ks = 0; ks < TC_N / 16; ks++) {
-              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-              umma_bf16(tmem_acc_u + (uint32_t)(TC_N / 2), ad0 + ainc, bd0 + brow + binc, idesc, ks > 0 ? 1u : 0u);
-            }
-            umma_commit(bar_done2 + 8 * t_u);                            // all of the layer's MMAs
-          }
-#endif
-          else {
-            const uint32_t idesc = umma_idesc<FMT>(nl);
-#pragma unroll
-            for (int ks = 0; ks < TC_N / 16; ks++) {
-              const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
-              const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
-              umma_bf16(tmem_acc_u, ad0 + ainc, bd0 + binc, idesc, ks > 0 ? 1u : 0u);
-            }
-          }
-#if AG_NHALF
-          // unsplit layers (head, swapped) complete both barriers at once, so that both advance one phase per layer
-          if (!(NHALF && !is_head && !(SW && swapped))) { umma_commit(bar_done + 8 * t_u); if (NHALF) umma_commit(bar_done2 + 8 * t_u); }
-#else
-          umma_commit(bar_done + 8 * t_u);
-#endif
-          if (NT == 2) umma_commit(bar_empty + 8 * s);                  // one tile: the requesting lane has itself seen the previous layer complete
-          if (wl == 0 && t_u == 0) umma_commit(bar_stagger);
+          tc_fence_before();
         }
-        __syncwarp();
-        if (ltr) lt2 = clock64();
-      }
-      // the weights two layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the issuer
-      // the request sat on the critical path: 2 k cycles per rollout)
-      if (warp == 1 && lane == 0 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
-      if (l == 0 && has_game) rnd_next = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
-      mbar_wait(bar_done + 8 * t, wl & 1);
-#if AG_NHALF
-      const bool split = NHALF && !is_head && !(SW && swapped);         // CTA-uniform: this layer was issued as two column halves
-      if (NHALF && !split) mbar_wait(bar_done2 + 8 * t, wl & 1);        // keeps the second barrier's phase in step on unsplit layers
-#endif
-      tc_fence_after();
-      long long lt3 = 0;
-      if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
-
-      if (SW && swapped && !is_head) {
-        if constexpr (SW) {
-          if (NS == 32) epilogue_swapped<FMT, 8, AG_KSPLIT>(tmem_acc, NS, wq, csb, lane, l, At, sres);
-          else epilogue_swapped<FMT, 16, AG_KSPLIT>(tmem_acc, NS, wq, csb, lane, l, At, sres);
-        }
-        tc_fence_before();
-        fence_proxy_async();
-        long long lt4 = 0;
-        if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
-        named_bar_sync(1 + t, 32 * WPT);
-        if (ltr) t_ly[4] += clock64() - lt4;
-      } else if (!is_head) {
-        // epilogue: b = relu(acc) (base) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b)
-        const bool keep = (l + 2 < nlayers);                            // the last trunk layer's residual is not read again
-#if AG_NHALF
-        uint4 pend[4];                                                  // operands of a first-half slice, held back
-        int pend_cs = -1;
-        bool waited2 = !split;
-        auto flush_pending = [&] {
-          if (!waited2) { mbar_wait(bar_done2 + 8 * t, wl & 1); tc_fence_after(); waited2 = true; }
-          if (pend_cs >= 0) {
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const int c = 4 * pend_cs + q;
-              *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pend[q];
-            }
-            pend_cs = -1;
-          }
-        };
-#pragma unroll
-        for (int ji = 0; ji < 2 * CPW; ji++) {
-          // slices of this warp: one in each column half when the layer is split, else csb, csb + 1
-          const int cs = NHALF ? (csb >> 1) + 2 * (ji >> 1) : csb + (ji >> 1);
-          const int i = ji & 1;
-          const bool hold = split && cs < 2;                            // a slice of the first half: its stores wait
-          if (split && !hold) flush_pending();                          // first touch of the second half: wait for its MMAs
-          const uint32_t lane_sel = lane_row + (uint32_t)(cs * 32);
-          uint32_t va[16], vh[16];
-          tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
-          if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; e++) {
-            const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
-            const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
-            vh[e] = __float_as_uint(hv);
-          }
-          if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh);
-#pragma unroll
-          for (int c2 = 0; c2 < 2; c2++) {
-            const int c = 4 * cs + 2 * i + c2;
-            const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[8 * c2 + 0]), __uint_as_float(vh[8 * c2 + 1])),
-                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 2]), __uint_as_float(vh[8 * c2 + 3])),
-                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 4]), __uint_as_float(vh[8 * c2 + 5])),
-                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 6]), __uint_as_float(vh[8 * c2 + 7])));
-            if (hold) { pend[2 * i + c2] = pk; pend_cs = cs; }
-            else *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
-          }
-        }
-        flush_pending();
-#else
-#pragma unroll
-        for (int ji = 0; ji < 2 * CPW; ji++) {
-          const int cs = csb + (ji >> 1), i = ji & 1;
-          const uint32_t lane_sel = lane_row + (uint32_t)(cs * 32);
-          uint32_t va[16], vh[16];
-          tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
-          if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 16; e++) {
-            const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
-            const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
-            vh[e] = __float_as_uint(hv);
-          }
-          if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh);
-#pragma unroll
-          for (int c2 = 0; c2 < 2; c2++) {
-            const int c = 4 * cs + 2 * i + c2;
-            const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[8 * c2 + 0]), __uint_as_float(vh[8 * c2 + 1])),
-                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 2]), __uint_as_float(vh[8 * c2 + 3])),
-                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 4]), __uint_as_float(vh[8 * c2 + 5])),
-                                        pack2<FMT>(__uint_as_float(vh[8 * c2 + 6]), __uint_as_float(vh[8 * c2 + 7])));
-            *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
-          }
-        }
-#endif
-        tmem_st_wait();
-        tc_fence_before();
-        fence_proxy_async();
-        long long lt4 = 0;
-        if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
-        named_bar_sync(1 + t, 32 * WPT);
-        if (ltr) t_ly[4] += clock64() - lt4;
-      } else {
-        // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> nn_out (global, read by the next search phase)
-        float* o = P.nn_out + (size_t)g_row * Lay::OUTS;
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          const int cs = csb;                                           // NH <= 32: only a warp's first slice can hold head columns
-          const uint32_t lane_sel = lane_row + (uint32_t)(cs * 32);
-          const int a0 = cs * 32 + i * 16;
-          if (a0 < T.NH) {                                              // warp-uniform
-            uint32_t v[16];
-            tmem_ld16(tmem_acc + lane_sel + 16 * i, v);
-            tmem_ld_wait();
-            float z[16];
-#pragma unroll
-            for (int e = 0; e < 16; e++) z[e] = __uint_as_float(v[e]) + sbias[a0 + e];
-            if (T.A >= a0 && T.A < a0 + 16) {
-#pragma unroll
-              for (int e = 0; e < 16; e++) if (a0 + e == T.A) z[e] = c_sigmoidf(z[e]);
-            }
-            if (g_row < L_end) {
-              float* so = SH.out + t * SH.out_tile_stride + r * Lay::OUTS;
-#pragma unroll
-              for (int q4 = 0; q4 < 4; q4++)
-                if (a0 + 4 * q4 < Lay::OUTS) {
-                  const float4 zv = make_float4(z[4 * q4], z[4 * q4 + 1], z[4 * q4 + 2], z[4 * q4 + 3]);
-                  *reinterpret_cast<float4*>(so + a0 + 4 * q4) = zv;
-                  if (last) *reinterpret_cast<float4*>(o + a0 + 4 * q4) = zv;     // the expand of the last rollout reads it from global memory
-                }
-            }
-          }
-        }
-        tc_fence_before();
       }
     }
-    __syncthreads();                                                   // nn_out (global) visible to the search phase
+    __syncthreads();                                                   // the outputs are visible to the search phase
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
   if (T.dbg && threadIdx.x == 0) {
@@ -552,10 +447,15 @@ __global__ void __launch_bounds__(FCfg<NT, WPT>::THREADS, (SW || WPT == 8) ? 1 :
   }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)
+  {
+    const int sg = threadIdx.x / W, sl = threadIdx.x & (W - 1);
+    const unsigned gm = group_mask<W>();
+    constexpr int GROUPS = C::THREADS / W;
 #pragma unroll 1
-  for (int p = 0; p < PASSES; p++) {
-    const int g = S.off + cta_first + p * GROUPS + sg;
-    if (g < L_end) expand_backup_game<G, false>(P, g, sl, gm, S.training, 1, nullptr, nullptr, S.cpuct);
+    for (int p = 0; p * GROUPS < count; p++) {
+      const int gl = p * GROUPS + sg;
+      if (gl < count) expand_backup_game<G, false>(P, g0 + gl, sl, gm, S.training, 1, nullptr, nullptr, S.cpuct);
+    }
   }
   __syncthreads();
   if (warp == 0) {

@@ -119,60 +119,41 @@ constexpr int PATH_SMEM_DEPTH = 16;          // path entries per game held in sh
 AG_D uint2 hot_ld_u2(const void* a) { return *reinterpret_cast<const uint2*>(a); }
 AG_D uint4 hot_ld_u4(const void* a) { return *reinterpret_cast<const uint4*>(a); }
 AG_D float4 hot_ld_f4(const void* a) { return *reinterpret_cast<const float4*>(a); }
+constexpr int BACKUP_LEVELS = 8;             // item lists of the backup phase: levels 0..6 of a path one list each, deeper levels share the last
 template <class G>
 struct RolloutShared {
   typename G::State* state;  // [GAMES] state of the leaf
+  typename G::State* root;   // [GAMES] state of the root: constant for the whole ply
   NodeHdr* hdr;              // [GAMES] header of the leaf as the descent saw it
+  Philox4* rnd;              // [GAMES] Philox block (depths 0..3) of the NEXT descent, computed under a network phase
   float* out;                // logits, value of the leaf: row gl at out + (gl / 128) * out_tile_stride + (gl % 128) * OUTS
   int out_tile_stride;       // (floats) the rows of a 128-game tile live in that tile's idle A-operand buffer
   int* d;                    // [GAMES] path length
   uint8_t* leaf;             // [GAMES]
   uint8_t* pn;               // [GAMES][PATH_SMEM_DEPTH] path nodes
   uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
-  unsigned char* nc_base;    // AG_TREE_SMEM: write-through copy of the descent fields of the first nc_nodes nodes of every game of the CTA,
-  int nc_nodes;              //   entry (gl, node) at nc_base + (gl * nc_nodes + node) * RootSlot<AP>::BYTES; 0 = no cache
+  int* lv_cnt;               // [BACKUP_LEVELS] items per level of the last descent (filled by the descents through shared-memory atomics)
+  uint16_t* lv_item;         // [BACKUP_LEVELS][GAMES] item = local game | path index << 8
+  int lv_stride;             // GAMES
+  unsigned char* nc_base;    // node cache of the small-batch kernel: write-through copy of the descent fields (header, child ids, π̄) of the
+  int nc_nodes;              //   first nc_nodes nodes of every game of the CTA; entry (gl, node) at nc_base + (gl * nc_nodes + node) * BYTES
 };
 
-// -DAG_TREE_SMEM=<KB> (development variant, NOT YET RUN ON A GPU): the small-batch per-ply kernel spends <KB> of shared memory on a
-// write-through cache of the descent fields (header, child ids, π̄ — the RootSlot layout) of the first nodes of each of its games.  In
-// the tail of a generation a CTA holds <= 32 games and a rollout is a latency chain; a level of the descent is then a shared-memory read
-// instead of an L2 round trip.  Every writer of those fields (node allocation in the descent, expand, the π̄ re-solve of the backup)
-// updates global memory as before AND the cache entry; global memory stays authoritative for everything else.
-#ifndef AG_TREE_SMEM
-#define AG_TREE_SMEM 0
-#endif
-#ifndef AG_DESC_LD128
-#define AG_DESC_LD128 0
-#endif
-// -DAG_PREFETCH=1 (development variant, NOT YET RUN ON A GPU): the full-load plies are bound by DRAM latency on L2 misses (live trees
-// 268 MB against 126 MB of L2, L2 hit rate 73 %) while DRAM bandwidth sits at 7 % — so spend bandwidth on lead time:
-//  - the backup item of a path node prefetches (to L2) the descent fields of all its children: the next descent, a whole network phase
-//    later, leaves the old path through one of them;
-//  - the descent prefetches the rest of every record it passes (visit counts, prior, q: bytes 64..REC), which its backup reads next.
-#ifndef AG_PREFETCH
-#define AG_PREFETCH 0
-#endif
-AG_D void prefetch_l2(const void* a) {
-#if AG_PREFETCH
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-#else
-  (void)a;
-#endif
-}
-template <int AP> struct RootSlot {
+// Node cache (small-batch per-ply kernel only).  In the tail of a generation a CTA holds <= 32 games and a rollout is a latency chain; the
+// descent fields of the first nodes of each game are kept in shared memory so that a level of the descent is a shared-memory read
+// instead of an L2 round trip (and the root, whose π̄ the backup has just rewritten, does not wait for that store to reach L2 and come
+// back).  Every writer of those fields (node allocation in the descent, expand, the π̄ re-solve of the backup) updates global memory as
+// before AND the cache entry; global memory stays authoritative for everything else.
+template <int AP> struct CacheSlot {
   static constexpr int OFF_CHILD = 8;                                  // after the 8-byte header
   static constexpr int OFF_POLICY = (8 + AP + 15) & ~15;
   static constexpr int BYTES = OFF_POLICY + 4 * AP;                    // 48 (AP = 8), 96 (AP = 16)
 };
 // cache entry of (local game gl, node) or nullptr
-template <class G>
+template <class G, bool CACHE>
 AG_D unsigned char* node_cache_slot(const RolloutShared<G>& SH, const int gl, const int node) {
-#if AG_TREE_SMEM
-  return node < SH.nc_nodes ? SH.nc_base + (size_t)(gl * SH.nc_nodes + node) * RootSlot<Layout<G>::APAD>::BYTES : nullptr;
-#else
-  (void)SH; (void)gl; (void)node;
-  return nullptr;
-#endif
+  if (!CACHE) return nullptr;
+  return node < SH.nc_nodes ? SH.nc_base + (size_t)(gl * SH.nc_nodes + node) * CacheSlot<Layout<G>::APAD>::BYTES : nullptr;
 }
 
 // One independent slice of the live games.  The rollout loop of a slice is replayed from a CUDA graph on its own stream, so
@@ -265,10 +246,7 @@ template <int AP> AG_D float sel_reg(const float (&v)[AP], const int idx) {
   return t[0];
 }
 
-// SPEC (the small-batch kernel, where a rollout is a latency chain): the quotients of the derivative are issued together with those of
-// the sum instead of after the convergence test — one batch of independent divisions per iteration instead of two dependent ones.  The
-// derivative of the last iteration is computed and dropped, as the reference does (:144-151 computes both in the same loop).
-template <int A, int AP, bool SPEC = false>
+template <int A, int AP>
 AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis)[AP], const int (&ch)[AP], const int (&ord)[AP],
                      const int nchild, const float cpuct, float (&pol)[AP], long long* tr = nullptr) {
   int nv = 0, acount = 0;
@@ -314,28 +292,17 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
 #pragma unroll
     for (int k = 0; k < A; k++) { bot[k] = fsub(alpha, qs[k]); bmin = fminf(bmin, bot[k]); bmax = fmaxf(bmax, bot[k]); }
     const bool fast = num_ok && bmin >= SQ_LO && bmax <= SQ_HI;                      // (a NaN denominator fails the comparison chain below)
-    float S, G = 0.f;
+    float S;
     if (fast) {
       // all quotients first — independent, branch-free, staged so that they overlap in the pipeline — then the adds in reference order
-      constexpr int NQ = SPEC ? 2 * (A + 1) : A + 1;
-      float na[NQ], nb[NQ], nq[NQ];
+      float na[A + 1], nb[A + 1], nq[A + 1];
       na[0] = rem; nb[0] = alpha;
 #pragma unroll
       for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = bot[k]; }
-      if (SPEC) {
-        na[A + 1] = rem; nb[A + 1] = fmul(alpha, alpha);
-#pragma unroll
-        for (int k = 0; k < A; k++) { na[A + 2 + k] = tops[k]; nb[A + 2 + k] = fmul(bot[k], bot[k]); }
-      }
-      fdiv_fast_n<NQ>(na, nb, nq);
+      fdiv_fast_n<A + 1>(na, nb, nq);
       S = nq[0];
 #pragma unroll
       for (int k = 0; k < A; k++) if (k < nchild) S = fadd(S, nq[k + 1]);
-      if (SPEC) {
-        G = nq[A + 1];
-#pragma unroll
-        for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[A + 2 + k]);
-      }
     } else {
       S = fdiv(rem, alpha);
 #pragma unroll
@@ -345,16 +312,14 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
     if (newerr < 0.001f || newerr == err) break;
     // the derivative is only needed when the iteration continues (the reference computes it in the same loop and drops it on exit)
     if (fast && alpha == alpha) {
-      if (!SPEC) {
-        float na[A + 1], nb[A + 1], nq[A + 1];
-        na[0] = rem; nb[0] = fmul(alpha, alpha);
+      float na[A + 1], nb[A + 1], nq[A + 1];
+      na[0] = rem; nb[0] = fmul(alpha, alpha);
 #pragma unroll
-        for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = fmul(bot[k], bot[k]); }
-        fdiv_fast_n<A + 1>(na, nb, nq);
-        G = nq[0];
+      for (int k = 0; k < A; k++) { na[k + 1] = tops[k]; nb[k + 1] = fmul(bot[k], bot[k]); }
+      fdiv_fast_n<A + 1>(na, nb, nq);
+      float G = nq[0];
 #pragma unroll
-        for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[k + 1]);
-      }
+      for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[k + 1]);
       alpha = fadd(alpha, fdiv(newerr, G));
     } else {
       float gs = fdiv(-rem, fmul(alpha, alpha));
@@ -654,7 +619,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // jj = index in the recorded path (0 = root), d = path length.  Each ancestor is a different node, so items are independent;
 // the value an ancestor receives is the leaf value flipped once per level below it (value = 1 - value, :324), evaluated as that
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
-template <class G, bool SPEC = false>
+template <class G>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
                       long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr,
                       unsigned char* s_cache_row = nullptr, const int nc_nodes = 0) {
@@ -698,10 +663,6 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
         }
-#if AG_PREFETCH
-#pragma unroll
-        for (int a = 0; a < A; a++) if (ch[a] != 0) prefetch_l2(gbase + (size_t)(ch[a] - 1) * REC);
-#endif
         const int nchild = reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR)->nchild;
         // running mean of the child's value from this node's point of view (:319-320)
         float qold = 0.f; int vold = 0;
@@ -725,19 +686,17 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
         long long tr1 = 0;
         if (tr) { tr1 = clock64() + (__float_as_int(qnew) & 0); tr[0] += tr1 - tr0; }
         if (!last_rollout) {
-          solve_node<A, AP, SPEC>(p, q, vis, ch, ord, nchild, cpuct, pol, tr);
+          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol, tr);
           if (tr) { tr[1] += clock64() + (__float_as_int(pol[0]) & 0) - tr1; tr[2] += 1; }
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
             *reinterpret_cast<float4*>(nrec + Lay::OFF_POLICY + 16 * c) = make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
-#if AG_TREE_SMEM
           if (s_cache_row != nullptr && nd < nc_nodes) {                              // write-through: π̄ of a cached node
 #pragma unroll
             for (int c = 0; c < AP / 4; c++)
-              *reinterpret_cast<float4*>(s_cache_row + nd * RootSlot<AP>::BYTES + RootSlot<AP>::OFF_POLICY + 16 * c) =
+              *reinterpret_cast<float4*>(s_cache_row + nd * CacheSlot<AP>::BYTES + CacheSlot<AP>::OFF_POLICY + 16 * c) =
                   make_float4(pol[4 * c], pol[4 * c + 1], pol[4 * c + 2], pol[4 * c + 3]);
           }
-#endif
         }
       }
     }
@@ -750,30 +709,35 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 // node) — measured on B200 the 8-lane descent of 223 games kept an SM's issue slots busy for 28 k cycles per rollout.  One thread
 // per game issues an eighth of the instructions; the seven-term prefix scan it serialises is shorter than the shuffles it replaces.
 // Same operations in the same order as select_game / expand_game: results are bit-identical.
+//
+// What the descent needs besides the tree comes from shared memory (RolloutShared): the root's state (constant for the ply; every
+// other state on the path is play() of it — a child's stored state IS play(parent state, action) — so no state is ever loaded), and
+// the Philox block of depths 0..3, computed ahead of time under the previous network phase.  The copies in global memory of what the
+// descent hands to the next phases (leaf, node count, path) are written on the last rollout of a ply — that is when the stand-alone
+// kernels and the read-back entry points look at them — and for path entries beyond the shared-memory window.
+// The walk only reads; the allocation of the new leaf (move generation, terminal test, nine stores) happens once, after the loop, when
+// the lanes of the warp have reconverged — inside the loop it was executed divergently, level after level, by whichever lanes had
+// reached their leaf.
+// CACHE: the small-batch kernel's node cache (above).
 // ------------------------------------------------------------------------------------------------
-// root: the root's state, held in a register by the game's thread for the whole ply.  rnd0: the Philox block of depths 0..3 of THIS rollout,
-// computed ahead of time (under the network phase of the previous rollout) so that it is off the descent's critical path.
-// The copies in global memory of what the descent hands to the next phases (leaf, node count, path) are written on the last rollout of a
-// ply — that is when the stand-alone kernels and the read-back entry points look at them — and for path entries beyond the shared-memory
-// window; during the loop they travel through shared memory only (a third of the descent's requests to the memory pipeline were these).
-template <class G>
+template <class G, bool CACHE>
 AG_D void select_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, const u32 uid, int& nn, int rollout, int last_rollout,
-                       u64 seed, u32 ply, const typename G::State& root, const Philox4& rnd0, long long* tr = nullptr) {
+                       u64 seed, u32 ply, long long* tr = nullptr) {
   const long long tr0 = tr ? clock64() : 0;
   long long trA = tr0, trB = tr0, trC = tr0, trD = tr0;
   typedef Layout<G> Lay;
+  typedef CacheSlot<Lay::APAD> CS;
   static_assert(Lay::FAST, "thread-per-game descent needs the stored policy");
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
   char* gbase = P.tree + (size_t)g * P.game_stride;
   int node = 0, depth = 0, rblock = 0;
-  Philox4 rnd = rnd0;
+  Philox4 rnd = SH.rnd[gl];
   uint8_t* pnode = P.path_node + (size_t)g * P.R;
   uint8_t* pmove = P.path_move + (size_t)g * P.R;
   uint2 hw;
-  // The state of the node the descent stands on is carried in registers and advanced with play() at every step — a child's stored
-  // state IS play(parent state, action), so the value is the same — instead of one more dependent round trip for the parent's state
-  // when the leaf is created.
-  typename G::State cur = root;
+  typename G::State cur = SH.root[gl];
+  int best = 0, nchild = 0;
+  bool create = false;
 
   while (true) {
     char* rec = gbase + (size_t)node * REC;
@@ -781,37 +745,24 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
     u64 cw0, cw1 = 0;
     float pol[AP];
-#if AG_TREE_SMEM
-    unsigned char* const csl = node_cache_slot<G>(SH, gl, node);                       // this node's cache entry, if it has one
-    const unsigned char* sl = csl;
-    if (sl != nullptr) {
+    const unsigned char* sl = node_cache_slot<G, CACHE>(SH, gl, node);                 // this node's cache entry, if it has one
+    if (CACHE && sl != nullptr) {
       hw = *reinterpret_cast<const uint2*>(sl);
-      const uint2 cv = *reinterpret_cast<const uint2*>(sl + RootSlot<AP>::OFF_CHILD);
+      const uint2 cv = *reinterpret_cast<const uint2*>(sl + CS::OFF_CHILD);
       cw0 = (u64)cv.x | ((u64)cv.y << 32);
       if (AP == 16) {
-        const uint2 cv1 = *reinterpret_cast<const uint2*>(sl + RootSlot<AP>::OFF_CHILD + 8);
+        const uint2 cv1 = *reinterpret_cast<const uint2*>(sl + CS::OFF_CHILD + 8);
         cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
       }
 #pragma unroll
       for (int c = 0; c < AP / 4; c++) {
-        const float4 pv = *reinterpret_cast<const float4*>(sl + RootSlot<AP>::OFF_POLICY + 16 * c);
+        const float4 pv = *reinterpret_cast<const float4*>(sl + CS::OFF_POLICY + 16 * c);
         pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
       }
-    } else
-#endif
-    {
+    } else {
       // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
-#if AG_DESC_LD128
-      // development variant (not yet run on a GPU): header and the first child word are the record's first 16 bytes — one 128-bit
-      // request instead of two 64-bit ones (the descent at full load is bound by the SM's load-request throughput)
-      static_assert(Lay::OFF_HDR % 16 == 0 && Lay::OFF_CHILD == Lay::OFF_HDR + 8, "header and child ids are adjacent");
-      const uint4 hc = hot_ld_u4(rec + Lay::OFF_HDR);
-      hw = make_uint2(hc.x, hc.y);
-      const uint2 cv = make_uint2(hc.z, hc.w);
-#else
       hw = hot_ld_u2(rec + Lay::OFF_HDR);
       const uint2 cv = hot_ld_u2(rec + Lay::OFF_CHILD);
-#endif
       cw0 = (u64)cv.x | ((u64)cv.y << 32);
       if (AP == 16) {
         const uint2 cv1 = hot_ld_u2(rec + Lay::OFF_CHILD + 8);
@@ -823,24 +774,15 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
         pol[4 * c] = pv.x; pol[4 * c + 1] = pv.y; pol[4 * c + 2] = pv.z; pol[4 * c + 3] = pv.w;
       }
     }
-#if AG_PREFETCH
-#pragma unroll
-    for (int o = 64; o < REC; o += 64) prefetch_l2(rec + o);                          // what this node's backup item will read
-#endif
-    // the uniform of this depth does not depend on the loads above: Philox runs while they are in flight
-    const long long tP0 = (tr && depth == 0) ? clock64() : 0;
+    // the uniform of this depth does not depend on the loads above: a Philox block beyond the first runs while they are in flight
     if ((depth >> 2) != rblock) { rblock = depth >> 2; rnd = philox4x32_10(uid, ply, (u32)rollout, (u32)rblock, (u32)seed, (u32)(seed >> 32)); }
     const int w = depth & 3;
     const float u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
-    if (tr && depth == 0) { tr[11] += clock64() + (__float_as_int(u) & 0) - tP0; tr[12] += tP0 - tr0; }
-    const int nchild = (int)((hw.x >> 16) & 0xFFu), flags = (int)(hw.x >> 24);
+    nchild = (int)((hw.x >> 16) & 0xFFu);
+    const int flags = (int)(hw.x >> 24);
     if (tr && depth == 0) trA = clock64() + (hw.x & 0) + (__float_as_int(pol[A - 1]) & 0) + ((u32)cw0 & 0);
-    if (!(flags & F_EXPANDED)) {                                                      // while expanded[nindex]==1  (:110)
-      // an existing node that is not expanded: the root before its first evaluation, or a terminal node
-      SH.state[gl] = cur;
-      *reinterpret_cast<uint2*>(&SH.hdr[gl]) = hw;
-      break;
-    }
+    if (!(flags & F_EXPANDED)) break;                                                 // while expanded[nindex]==1  (:110): the root before its
+                                                                                      // first evaluation, or a terminal node
     if (node == 0 && last_rollout) {                                                  // copy_pol (:330-339)
 #pragma unroll
       for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pol[a];
@@ -848,7 +790,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     if (tr && depth == 0) trB = clock64() + (__float_as_int(u) & 0);
     // inverse-CDF scan in ascending action order (:172-182)
     float cum = 0.f;
-    int best = -1;
+    best = -1;
     bool done = false;
 #pragma unroll
     for (int a = 0; a < A; a++) {
@@ -863,48 +805,58 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     if (tr && depth == 0) trC = clock64() + (best & 0);
     if (last_rollout || depth >= PATH_SMEM_DEPTH) { pnode[depth] = (uint8_t)node; pmove[depth] = (uint8_t)best; }
     if (depth < PATH_SMEM_DEPTH) { SH.pn[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)node; SH.pm[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)best; }
-    int c = (int)(((AP == 16 && best >= 8 ? cw1 : cw0) >> (8 * (best & 7))) & 0xFFu);
-    if (c == 0) {                                                                     // allocate the child (:183-191)
-      nn += 1;
-      c = nn;
-      *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
-      *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
-      reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
-      const typename G::State ns = G::play(cur, best + 1);
-      int res = 0;
-      const bool term = G::is_over(ns, res);
-      char* nrec = gbase + (size_t)(c - 1) * REC;
-#pragma unroll
-      for (int k = 0; k < AP / 4; k++) *reinterpret_cast<float4*>(nrec + Lay::OFF_Q + 16 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int k = 0; k < AP / 8; k++) {
-        *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
-      }
-      state_store(nrec + Lay::OFF_STATE, ns);
-      const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
-      hdr_store(nrec + Lay::OFF_HDR, nhw);
-#if AG_TREE_SMEM
-      if (csl != nullptr) {                                                            // the parent's entry: child id and child count
-        csl[RootSlot<AP>::OFF_CHILD + best] = (uint8_t)c;
-        csl[2] = (uint8_t)(nchild + 1);                                                // NodeHdr::nchild
-      }
-      if (unsigned char* nsl = node_cache_slot<G>(SH, gl, c - 1)) {                    // the new node's entry (π̄ is written by expand)
-        hdr_store(nsl, nhw);
-#pragma unroll
-        for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint2*>(nsl + RootSlot<AP>::OFF_CHILD + 8 * k) = make_uint2(0, 0);
-      }
-#endif
-      SH.state[gl] = ns;
-      hdr_store(&SH.hdr[gl], nhw);
-      node = c - 1;
-      depth += 1;
-      break;
+    {                                                                                  // this (game, ancestor) is an item of the next backup phase
+      const int lv = depth < BACKUP_LEVELS ? depth : BACKUP_LEVELS - 1;
+      const int slot = atomicAdd(&SH.lv_cnt[lv], 1);
+      SH.lv_item[lv * SH.lv_stride + slot] = (uint16_t)(gl | (depth << 8));
     }
+    const int c = (int)(((AP == 16 && best >= 8 ? cw1 : cw0) >> (8 * (best & 7))) & 0xFFu);
+    if (c == 0) { create = true; break; }                                              // the child does not exist yet: allocate it below
     node = c - 1;                                                                      // :192
     depth += 1;
     cur = G::play(cur, best + 1);
     if (tr && depth == 1) trD = clock64() + (node & 0);
+  }
+
+  if (create) {                                                                        // allocate the child (:183-191)
+    char* rec = gbase + (size_t)node * REC;
+    nn += 1;
+    const int c = nn;
+    *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
+    *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
+    reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
+    const typename G::State ns = G::play(cur, best + 1);
+    int res = 0;
+    const bool term = G::is_over(ns, res);
+    char* nrec = gbase + (size_t)(c - 1) * REC;
+#pragma unroll
+    for (int k = 0; k < AP / 4; k++) *reinterpret_cast<float4*>(nrec + Lay::OFF_Q + 16 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < AP / 8; k++) {
+      *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
+    }
+    state_store(nrec + Lay::OFF_STATE, ns);
+    const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
+    hdr_store(nrec + Lay::OFF_HDR, nhw);
+    if (CACHE) {
+      if (unsigned char* csl = node_cache_slot<G, CACHE>(SH, gl, node)) {              // the parent's entry: child id and child count
+        csl[CS::OFF_CHILD + best] = (uint8_t)c;
+        csl[2] = (uint8_t)(nchild + 1);                                                // NodeHdr::nchild
+      }
+      if (unsigned char* nsl = node_cache_slot<G, CACHE>(SH, gl, c - 1)) {             // the new node's entry (π̄ is written by expand)
+        hdr_store(nsl, nhw);
+#pragma unroll
+        for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint2*>(nsl + CS::OFF_CHILD + 8 * k) = make_uint2(0, 0);
+      }
+    }
+    SH.state[gl] = ns;
+    hdr_store(&SH.hdr[gl], nhw);
+    node = c - 1;
+    depth += 1;
+  } else {
+    SH.state[gl] = cur;
+    *reinterpret_cast<uint2*>(&SH.hdr[gl]) = hw;
   }
   if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }
   SH.leaf[gl] = (uint8_t)node;
@@ -917,25 +869,26 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)depth); atomicAdd(&P.counters[1], 1ull); }
 }
 
-template <class G>
-AG_D LeafEval expand_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, int training, int last_rollout) {
+// expand (mcts_gpu.jl:250-302) + softmax! (:417) of the leaf of local game gl, by one thread; everything it needs about the leaf is in
+// shared memory (RolloutShared).  Returns nothing: the backup items read the leaf's value and terminal flag from the same place.
+template <class G, bool CACHE>
+AG_D void expand_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, int training, int last_rollout) {
   typedef Layout<G> Lay;
+  typedef CacheSlot<Lay::APAD> CS;
   static_assert(Lay::FAST, "thread-per-game expand is written for the FAST record");
   constexpr int A = G::A, REC = Lay::REC, AP = Lay::APAD;
   const int leaf = SH.leaf[gl];
   char* rec = P.tree + (size_t)g * P.game_stride + (size_t)leaf * REC;
   const NodeHdr h = SH.hdr[gl];
+  if ((h.flags & F_TERMINAL) != 0) return;
   const typename G::State st = SH.state[gl];
-  const bool term = (h.flags & F_TERMINAL) != 0;
-  float v = 0.f;
-  if (!term) {                                                                         // expand: :258-296, softmax! :417
+  {                                                                                    // expand: :258-296, softmax! :417
     float x[Lay::OUTS];
 #pragma unroll
     for (int c = 0; c < Lay::OUTS / 4; c++) {
       const float4 ov = *reinterpret_cast<const float4*>(SH.out + (gl >> 7) * SH.out_tile_stride + (gl & 127) * Lay::OUTS + 4 * c);
       x[4 * c] = ov.x; x[4 * c + 1] = ov.y; x[4 * c + 2] = ov.z; x[4 * c + 3] = ov.w;
     }
-    v = x[A];
     float m = -__int_as_float(0x7f800000);
 #pragma unroll
     for (int a = 0; a < A; a++) m = fmaxf(m, x[a]);
@@ -998,18 +951,27 @@ AG_D LeafEval expand_game1(const SearchParams& P, const int g, const int gl, con
       for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pr[a];
     }
     reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
-#if AG_TREE_SMEM
-    if (unsigned char* sl = node_cache_slot<G>(SH, gl, leaf)) {                          // write-through: π̄ = prior, expanded flag
+    if (CACHE) {
+      if (unsigned char* sl = node_cache_slot<G, CACHE>(SH, gl, leaf)) {                 // write-through: π̄ = prior, expanded flag
 #pragma unroll
-      for (int c = 0; c < AP / 4; c++)
-        *reinterpret_cast<float4*>(sl + RootSlot<AP>::OFF_POLICY + 16 * c) = make_float4(pr[4 * c], pr[4 * c + 1], pr[4 * c + 2], pr[4 * c + 3]);
-      sl[3] = (uint8_t)(h.flags | F_EXPANDED);                                           // NodeHdr::flags
+        for (int c = 0; c < AP / 4; c++)
+          *reinterpret_cast<float4*>(sl + CS::OFF_POLICY + 16 * c) = make_float4(pr[4 * c], pr[4 * c + 1], pr[4 * c + 2], pr[4 * c + 3]);
+        sl[3] = (uint8_t)(h.flags | F_EXPANDED);                                         // NodeHdr::flags
+      }
     }
-#endif
   }
+}
+
+// what a backup item needs to know about the leaf of its game, from the shared-memory hand-off
+template <class G>
+AG_D LeafEval leaf_eval1(const RolloutShared<G>& SH, const int gl) {
+  typedef Layout<G> Lay;
+  const NodeHdr h = SH.hdr[gl];
   LeafEval E;
-  E.v = v; E.term = term ? 1 : 0; E.parent = h.parent; E.action = h.action;
-  E.value0_d = (double)(1 + (int)(int8_t)(st.player * h.result)) * 0.5;
+  E.term = (h.flags & F_TERMINAL) ? 1 : 0;
+  E.v = SH.out[(gl >> 7) * SH.out_tile_stride + (gl & 127) * Lay::OUTS + G::A];
+  E.parent = h.parent; E.action = h.action;
+  E.value0_d = (double)(1 + (int)(int8_t)(SH.state[gl].player * h.result)) * 0.5;
   return E;
 }
 
