@@ -1,13 +1,16 @@
 // fused.cuh — one persistent kernel per ply: the whole R-rollout loop of mcts_single (mcts_gpu.jl:396-439) on chip.
 //
-// A CTA of 512 threads (16 warps x 128 registers) owns up to 256 games for the entire search of a ply and alternates, per rollout,
+// A CTA of 16 worker warps (+ one warp that only issues tcgen05.mma and requests weights) owns up to 256 games for the entire search of
+// a ply and alternates, per rollout,
 //   search phase : ONE POOL of warp-sized work units drawn from a shared-memory counter — the (game, ancestor) items of backUp + the
 //                  α re-solve (search.cuh: backup_item), listed level by level by the descents that produced them, and the expansion of
 //                  the leaves (expand_game1), 32 games per unit — then, behind one barrier, the descent of the next rollout, one thread
 //                  per game (select_game1).  Everything a phase hands to the next lives in shared memory (RolloutShared).
 //   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves.  All 16 warps serve one 128-row tile at a time — TMEM
 //                  lane quarter w%4, 32-column slice w/4 — and with two tiles (129..256 games) they ALTERNATE: the epilogue of tile 0
-//                  runs under the MMAs of tile 1 and vice versa, so the tensor pipe and the epilogue warps are both busy.  The fp32
+//                  runs under the MMAs of tile 1 and vice versa, so the tensor pipe and the epilogue warps are both busy.  Issuing a
+//                  layer's eight tcgen05.mma takes the issuing thread 600-1200 cycles, which is why it is a warp of its own, told
+//                  through an mbarrier when a tile's next operand is in shared memory, and not one of the epilogue warps.  The fp32
 //                  residual stream lives in TMEM (ordinary orientation) or in registers (swapped orientation); weights stream
 //                  global -> shared through a bulk-copy ring that never drains between rollouts.
 // Games of a CTA depend on each other only through their shared GEMM tile, so there is no grid-wide barrier and no kernel boundary
@@ -25,7 +28,12 @@ using namespace tc;
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
 template <class G, int NT> struct FCfg {
-  static constexpr int THREADS = 512;
+  static constexpr int WORKERS = 512;                                  // 16 worker warps: search pool, descent, epilogues
+  // Two tiles: + a warp that only issues tcgen05.mma and requests weights (the register file then holds 20 warps x 96 registers).
+  // One tile: the layers are a serial chain anyway — MMAs, then the epilogue that produces the next operand — so worker warp 0 issues
+  // in line and the workers keep 128 registers.
+  static constexpr bool ISSUE_WARP = NT == 2;
+  static constexpr int THREADS = WORKERS + (ISSUE_WARP ? 32 : 0);
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * BACKUP_LEVELS + 1 + 2 * PATH_SMEM_DEPTH;
@@ -138,7 +146,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   unsigned char* sA = smem;                                            // [NT][32 KB] activations (A operands)
   unsigned char* sW = smem + NT * TC_A_BYTES;                          // [STAGES][32 KB] weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * TC_W_STAGE_BYTES);
-  // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile
+  // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile, [8..9] a_ready per tile (the tile's next A operand is in shared memory)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   int* s_next = reinterpret_cast<int*>(bars + 17);                     // [2] work-unit counters of the search pool, by rollout parity
   int* s_lvcnt = reinterpret_cast<int*>(bars + 18);                    // [2][BACKUP_LEVELS] items per level, by rollout parity
@@ -168,11 +176,13 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   SH.nc_nodes = SMALL ? min(P.R, C::TREE_BYTES / (CacheSlot<Lay::APAD>::BYTES * count)) : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6);
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_ready = smem_u32(bars + 8);
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);                // warp-uniform, and visibly so to the compiler
+  const bool is_issuer = C::ISSUE_WARP && warp_u == C::WORKERS / 32;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < NT; t++) mbar_init(bar_done + 8 * t, 1);
+    for (int t = 0; t < NT; t++) { mbar_init(bar_done + 8 * t, 1); mbar_init(bar_ready + 8 * t, 1); }
     fence_barrier_init();
     s_next[0] = s_next[1] = 0;
     for (int i = 0; i < 2 * BACKUP_LEVELS; i++) s_lvcnt[i] = 0;
@@ -194,9 +204,6 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     mbar_expect_tx(bar_full + 8 * s, bytes);
     bulk_g2s(smem_u32(sW + s * TC_W_STAGE_BYTES), T.img + (size_t)l * TC_W_STAGE_BYTES, bytes, bar_full + 8 * s);
   };
-  if (threadIdx.x == 32) {                                             // fill the ring: STAGES - 1 layers ahead
-    for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
-  }
 
   // ---- roles ----
   // network: TMEM lane quarter and 32-column slice of this warp; its thread carries row r of whichever tile is being served
@@ -205,14 +212,13 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   // The MMA-issuing warp takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived from values
   // the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent `lane == 0` branch each
   // MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const bool issuer_warp = warp_u == 0;
   const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
   // one thread per game for the descent: the game's uid and node count stay in its registers for the whole ply; the root's state and the
   // first Philox block of the coming descent wait in shared memory
   const bool has_game = (int)threadIdx.x < count;
+  const unsigned game_mask = __ballot_sync(0xffffffffu, has_game);      // the lanes of this warp that descend
   const int my_g = g0 + (int)threadIdx.x;
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
@@ -269,8 +275,26 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     __syncwarp();
   };
 
-  int wl = 0;                                                          // global layer counter (ring / barrier phases)
-  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: weights wait, MMA issue, MMA done, epilogue, barrier
+  if (!C::ISSUE_WARP && threadIdx.x == 32) {                           // fill the ring: STAGES - 1 layers ahead
+    for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
+  }
+  if (is_issuer) {
+    // ---- the issue warp: for every layer and tile, wait until the workers have put the tile's operand in shared memory, issue the layer's
+    //      MMAs, and keep the weight ring STAGES - 1 layers ahead ----
+    if (elect_one()) for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
+    __syncwarp();
+    for (int wl_ = 0; wl_ < total_layers; wl_++) {
+      const int l = wl_ % nlayers;
+      for (int t = 0; t < ntiles; t++) {
+        mbar_wait(bar_ready + 8 * t, wl_ & 1);
+        if (t == 0) mbar_wait(bar_full + 8 * (wl_ % STAGES), (wl_ / STAGES) & 1);
+        issue_layer(t, l, wl_);
+      }
+      if (wl_ + STAGES - 1 < total_layers) { if (elect_one()) load_layer(wl_ + STAGES - 1); __syncwarp(); }
+    }
+  } else {
+  int wl = 0;                                                          // global layer counter (barrier phases)
+  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: -, -, MMA done wait, epilogue, barrier
   long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): -, -, search pool, descent, network
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
@@ -286,6 +310,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         s_next[par ^ 1] = 0;
         for (int lv = 0; lv < BACKUP_LEVELS; lv++) s_lvcnt[(par ^ 1) * BACKUP_LEVELS + lv] = 0;
       }
+      const long long w_t0 = T.dbg ? clock64() : 0;                    // development trace: per-warp busy time in the pool
       int n_items = 0;
 #pragma unroll
       for (int lv = 0; lv < BACKUP_LEVELS; lv++) n_items += cnt[lv];
@@ -304,7 +329,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
             const int item = SH.lv_item[lv * C::GAMES + (i - base)];
             const int gl = item & 0xFF, jj = item >> 8;
             const LeafEval E = leaf_eval1<G>(SH, gl);
-            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr,
+            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr,
                            SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
                            SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
           }
@@ -313,13 +338,16 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           if (gl < count) expand_game1<G, SMALL>(P, g0 + gl, gl, SH, S.training, 0);
         }
       }
-      __syncthreads();
+      if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 32 + warp] += clock64() - w_t0;
+      named_bar_sync(1, C::WORKERS);
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // descent of this rollout; its path nodes are listed as the items of the next pool (parity k)
     SH.lv_cnt = s_lvcnt + (k & 1) * BACKUP_LEVELS;
-    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 32 + 8 : nullptr);
-    __syncthreads();
+    const long long w_t1 = T.dbg ? clock64() : 0;                      // development trace: per-warp time in the descent
+    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr);
+    if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 48 + warp] += clock64() - w_t1;
+    named_bar_sync(1, C::WORKERS);
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
@@ -350,20 +378,13 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
       }
     }
     fence_proxy_async();
-    __syncthreads();
-    // base layer of every tile
-    {
-      long long lt0 = 0;
-      const bool ltr = T.dbg != nullptr && threadIdx.x == 0;
-      if (ltr) lt0 = clock64();
-      if (issuer_warp) {
-        mbar_wait(bar_full + 8 * (wl % STAGES), (wl / STAGES) & 1);
-        for (int t = 0; t < ntiles; t++) issue_layer(t, 0, wl);
-      }
-      if (ltr) t_ly[1] += clock64() - lt0;
+    named_bar_sync(1, C::WORKERS);
+    if (C::ISSUE_WARP) {
+      if (threadIdx.x == 0) for (int t = 0; t < ntiles; t++) mbar_arrive(bar_ready + 8 * t);   // the issue warp: base layer of every tile
+    } else {
+      if (warp_u == 0) { mbar_wait(bar_full + 8 * (wl % STAGES), (wl / STAGES) & 1); issue_layer(0, 0, wl); }
+      if (threadIdx.x == 32 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
     }
-    // the weights STAGES - 1 layers ahead are requested by a lane that would otherwise just wait for MMAs
-    if (threadIdx.x == 32 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
     // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run
     if (has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
 
@@ -390,18 +411,14 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           tc_fence_before();
           fence_proxy_async();
           if (ltr && t == 0) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
-          __syncthreads();                                             // every warp has written its part of the next A operand of tile t
-          if (ltr && t == 0) t_ly[4] += clock64() - lt4;
-          // next layer of tile t: its MMAs run under the epilogue of the other tile
-          if (issuer_warp) {
-            long long lt0 = 0, lt1 = 0;
-            if (ltr && t == 0) lt0 = clock64();
-            if (t == 0) mbar_wait(bar_full + 8 * ((wl + 1) % STAGES), ((wl + 1) / STAGES) & 1);
-            if (ltr && t == 0) { lt1 = clock64(); t_ly[0] += lt1 - lt0; }
-            issue_layer(t, l + 1, wl + 1);
-            if (ltr && t == 0) t_ly[1] += clock64() - lt1;
+          named_bar_sync(1, C::WORKERS);                               // every warp has written its part of the next A operand of tile t
+          if (C::ISSUE_WARP) {
+            if (threadIdx.x == 0) mbar_arrive(bar_ready + 8 * t);      // next layer of tile t: its MMAs run under the epilogue of the other tile
+          } else {
+            if (warp_u == 0) { mbar_wait(bar_full + 8 * ((wl + 1) % STAGES), ((wl + 1) / STAGES) & 1); issue_layer(0, l + 1, wl + 1); }
+            if (threadIdx.x == 32 && wl + STAGES < total_layers) load_layer(wl + STAGES);
           }
-          if (t == ntiles - 1 && threadIdx.x == 32 && wl + STAGES < total_layers) load_layer(wl + STAGES);
+          if (ltr && t == 0) t_ly[4] += clock64() - lt4;
         } else {
           // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> shared memory (read by the next search phase)
           const int gl = t * TC_TILE_M + r;
@@ -437,26 +454,27 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         }
       }
     }
-    __syncthreads();                                                   // the outputs are visible to the search phase
+    named_bar_sync(1, C::WORKERS);                                     // the outputs are visible to the search phase
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
   if (T.dbg && threadIdx.x == 0) {
-    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 32 + i] = t_ph[i];
-    T.dbg[blockIdx.x * 32 + 5] = count; T.dbg[blockIdx.x * 32 + 6] = visits;
-    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 32 + 24 + i] = t_ly[i];
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 64 + i] = t_ph[i];
+    T.dbg[blockIdx.x * 64 + 5] = count; T.dbg[blockIdx.x * 64 + 6] = visits;
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 64 + 24 + i] = t_ly[i];
   }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)
   {
     const int sg = threadIdx.x / W, sl = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
-    constexpr int GROUPS = C::THREADS / W;
+    constexpr int GROUPS = C::WORKERS / W;
 #pragma unroll 1
     for (int p = 0; p * GROUPS < count; p++) {
       const int gl = p * GROUPS + sg;
       if (gl < count) expand_backup_game<G, false>(P, g0 + gl, sl, gm, S.training, 1, nullptr, nullptr, S.cpuct);
     }
   }
+  }   // workers
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();

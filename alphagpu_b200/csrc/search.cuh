@@ -722,7 +722,7 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 // ------------------------------------------------------------------------------------------------
 template <class G, bool CACHE>
 AG_D void select_game1(const SearchParams& P, const int g, const int gl, const RolloutShared<G>& SH, const u32 uid, int& nn, int rollout, int last_rollout,
-                       u64 seed, u32 ply, long long* tr = nullptr) {
+                       u64 seed, u32 ply, const unsigned gmask, long long* tr = nullptr) {
   const long long tr0 = tr ? clock64() : 0;
   long long trA = tr0, trB = tr0, trC = tr0, trD = tr0;
   typedef Layout<G> Lay;
@@ -805,11 +805,6 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     if (tr && depth == 0) trC = clock64() + (best & 0);
     if (last_rollout || depth >= PATH_SMEM_DEPTH) { pnode[depth] = (uint8_t)node; pmove[depth] = (uint8_t)best; }
     if (depth < PATH_SMEM_DEPTH) { SH.pn[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)node; SH.pm[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)best; }
-    {                                                                                  // this (game, ancestor) is an item of the next backup phase
-      const int lv = depth < BACKUP_LEVELS ? depth : BACKUP_LEVELS - 1;
-      const int slot = atomicAdd(&SH.lv_cnt[lv], 1);
-      SH.lv_item[lv * SH.lv_stride + slot] = (uint16_t)(gl | (depth << 8));
-    }
     const int c = (int)(((AP == 16 && best >= 8 ? cw1 : cw0) >> (8 * (best & 7))) & 0xFFu);
     if (c == 0) { create = true; break; }                                              // the child does not exist yet: allocate it below
     node = c - 1;                                                                      // :192
@@ -861,6 +856,22 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }
   SH.leaf[gl] = (uint8_t)node;
   SH.d[gl] = depth;
+  {
+    // The (game, path index) pairs of this descent are the items of the next backup phase: listed level by level, with one shared-memory
+    // atomic per warp and level (the lanes of the warp — gmask — have reconverged here).
+    __syncwarp(gmask);
+    const int lane = (int)(threadIdx.x & 31);
+    const int maxd = (int)__reduce_max_sync(gmask, (unsigned)depth);
+    for (int lv = 0; lv < maxd; lv++) {
+      const int L = lv < BACKUP_LEVELS ? lv : BACKUP_LEVELS - 1;
+      const unsigned m = __ballot_sync(gmask, depth > lv);
+      const int leader = __ffs((int)m) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&SH.lv_cnt[L], __popc(m));
+      base = __shfl_sync(gmask, base, leader);
+      if (depth > lv) SH.lv_item[L * SH.lv_stride + base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(gl | (lv << 8));
+    }
+  }
   if (last_rollout) {
     P.leaf[g] = node;                                                                  // :195
     P.nnodes[g] = nn;

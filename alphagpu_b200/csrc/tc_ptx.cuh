@@ -24,6 +24,7 @@ AG_D void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.
 AG_D void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+AG_D void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 AG_D void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   do {
