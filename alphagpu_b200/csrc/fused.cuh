@@ -1,18 +1,19 @@
 // fused.cuh — one persistent kernel per ply: the whole R-rollout loop of mcts_single (mcts_gpu.jl:396-439) on chip.
 //
-// A CTA of 16 worker warps (+ one warp that only issues tcgen05.mma and requests weights) owns up to 256 games for the entire search of
-// a ply and alternates, per rollout,
+// A CTA of 512 threads (16 warps x 128 registers) owns up to 256 games for the entire search of a ply and alternates, per rollout,
 //   search phase : ONE POOL of warp-sized work units drawn from a shared-memory counter — the (game, ancestor) items of backUp + the
 //                  α re-solve (search.cuh: backup_item), listed level by level by the descents that produced them, and the expansion of
 //                  the leaves (expand_game1), 32 games per unit — then, behind one barrier, the descent of the next rollout, one thread
 //                  per game (select_game1).  Everything a phase hands to the next lives in shared memory (RolloutShared).
-//   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves.  All 16 warps serve one 128-row tile at a time — TMEM
-//                  lane quarter w%4, 32-column slice w/4 — and with two tiles (129..256 games) they ALTERNATE: the epilogue of tile 0
-//                  runs under the MMAs of tile 1 and vice versa, so the tensor pipe and the epilogue warps are both busy.  Issuing a
-//                  layer's eight tcgen05.mma takes the issuing thread 600-1200 cycles, which is why it is a warp of its own, told
-//                  through an mbarrier when a tile's next operand is in shared memory, and not one of the epilogue warps.  The fp32
-//                  residual stream lives in TMEM (ordinary orientation) or in registers (swapped orientation); weights stream
+//   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves, 128 games per tile.  Two tiles (129..256 games): 8 warps
+//                  per tile — TMEM lane quarter w%4, two 32-column slices each — with their own MMA issuer, tile 1 trailing tile 0 by one
+//                  MMA phase so that one tile's epilogue runs under the other's MMAs.  One tile: all 16 warps on it, one slice each.
+//                  The fp32 residual stream lives in TMEM (ordinary orientation) or in registers (swapped orientation); weights stream
 //                  global -> shared through a bulk-copy ring that never drains between rollouts.
+//                  (Measured alternatives, B200: all 16 warps alternating between the two tiles — 32 k cycles per rollout against 25 k,
+//                  because issuing a layer's eight tcgen05.mma occupies the issuing warp for 600-1200 cycles and the other 15 wait for
+//                  its share of the epilogue; the same with a 17th, issue-only warp — the register file then holds 20 warps x 96
+//                  registers and the search phases pay for it.)
 // Games of a CTA depend on each other only through their shared GEMM tile, so there is no grid-wide barrier and no kernel boundary
 // inside a ply: the per-rollout cost is the on-chip critical path instead of three launches plus their tails.
 #pragma once
@@ -28,12 +29,9 @@ using namespace tc;
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
 template <class G, int NT> struct FCfg {
-  static constexpr int WORKERS = 512;                                  // 16 worker warps: search pool, descent, epilogues
-  // Two tiles: + a warp that only issues tcgen05.mma and requests weights (the register file then holds 20 warps x 96 registers).
-  // One tile: the layers are a serial chain anyway — MMAs, then the epilogue that produces the next operand — so worker warp 0 issues
-  // in line and the workers keep 128 registers.
-  static constexpr bool ISSUE_WARP = NT == 2;
-  static constexpr int THREADS = WORKERS + (ISSUE_WARP ? 32 : 0);
+  static constexpr int THREADS = 512;
+  static constexpr int WPT = 16 / NT;                                  // warps per tile
+  static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * BACKUP_LEVELS + 1 + 2 * PATH_SMEM_DEPTH;
@@ -146,12 +144,12 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   unsigned char* sA = smem;                                            // [NT][32 KB] activations (A operands)
   unsigned char* sW = smem + NT * TC_A_BYTES;                          // [STAGES][32 KB] weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * TC_W_STAGE_BYTES);
-  // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile, [8..9] a_ready per tile (the tile's next A operand is in shared memory)
+  // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile, [8] stagger (one-shot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
-  int* s_next = reinterpret_cast<int*>(bars + 17);                     // [2] work-unit counters of the search pool, by rollout parity
-  int* s_lvcnt = reinterpret_cast<int*>(bars + 18);                    // [2][BACKUP_LEVELS] items per level, by rollout parity
-  float* sbias = reinterpret_cast<float*>(bars + 18) + 2 * BACKUP_LEVELS;   // [128] head biases
-  static_assert(18 * 8 + 2 * BACKUP_LEVELS * 4 + TC_N * 4 <= 1024, "fixed part of the work area");
+  int* s_next = reinterpret_cast<int*>(bars + 17);                     // [2] work-unit counters of the search pool, by rollout parity (+ [2] development)
+  int* s_lvcnt = reinterpret_cast<int*>(bars + 19);                    // [2][BACKUP_LEVELS] items per level, by rollout parity
+  float* sbias = reinterpret_cast<float*>(bars + 19) + 2 * BACKUP_LEVELS;   // [128] head biases
+  static_assert(19 * 8 + 2 * BACKUP_LEVELS * 4 + TC_N * 4 <= 1024, "fixed part of the work area");
   // hand-off between the phases of a rollout (search.cuh: RolloutShared)
   RolloutShared<G> SH;
   SH.state = reinterpret_cast<State*>(reinterpret_cast<unsigned char*>(bars) + 1024);      // 16-byte aligned
@@ -176,15 +174,14 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   SH.nc_nodes = SMALL ? min(P.R, C::TREE_BYTES / (CacheSlot<Lay::APAD>::BYTES * count)) : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_ready = smem_u32(bars + 8);
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);                // warp-uniform, and visibly so to the compiler
-  const bool is_issuer = C::ISSUE_WARP && warp_u == C::WORKERS / 32;
+  const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-    for (int t = 0; t < NT; t++) { mbar_init(bar_done + 8 * t, 1); mbar_init(bar_ready + 8 * t, 1); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, ntiles); }
+    for (int t = 0; t < NT; t++) mbar_init(bar_done + 8 * t, 1);
+    mbar_init(bar_stagger, 1);
     fence_barrier_init();
-    s_next[0] = s_next[1] = 0;
+    s_next[0] = s_next[1] = s_next[2] = s_next[3] = 0;
     for (int i = 0; i < 2 * BACKUP_LEVELS; i++) s_lvcnt[i] = 0;
   }
   if (threadIdx.x < TC_N) sbias[threadIdx.x] = T.bias[threadIdx.x];
@@ -206,12 +203,19 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   };
 
   // ---- roles ----
-  // network: TMEM lane quarter and 32-column slice of this warp; its thread carries row r of whichever tile is being served
-  const int wq = warp & 3, cs = warp >> 2;
+  // network: tile, TMEM lane quarter, first 32-column slice of this warp; its thread carries row r of its tile
+  constexpr int WPT = C::WPT, CPW = C::CPW;
+  const int t = warp / WPT, wq = warp & 3, csb = ((warp >> 2) & (WPT / 4 - 1)) * CPW;
   const int r = wq * 32 + lane;
-  // The MMA-issuing warp takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived from values
-  // the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent `lane == 0` branch each
-  // MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
+  unsigned char* At = sA + t * TC_A_BYTES;
+  const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
+  const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
+  // The MMA-issuing warp of a tile takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived
+  // from values the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent
+  // `lane == 0` branch each MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int t_u = warp_u / WPT;
+  const bool issuer_warp = (warp_u % WPT) == 0;
   const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
@@ -270,31 +274,16 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         }
       }
       umma_commit(bar_done + 8 * t);
-      if (t == ntiles - 1) umma_commit(bar_empty + 8 * s);              // the stage is free once the last tile's MMAs of this layer are done
+      umma_commit(bar_empty + 8 * s);                                   // the stage is free once every tile's MMAs of this layer are done
     }
     __syncwarp();
   };
 
-  if (!C::ISSUE_WARP && threadIdx.x == 32) {                           // fill the ring: STAGES - 1 layers ahead
+  if (threadIdx.x == 32) {                                             // fill the ring: STAGES - 1 layers ahead
     for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
   }
-  if (is_issuer) {
-    // ---- the issue warp: for every layer and tile, wait until the workers have put the tile's operand in shared memory, issue the layer's
-    //      MMAs, and keep the weight ring STAGES - 1 layers ahead ----
-    if (elect_one()) for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
-    __syncwarp();
-    for (int wl_ = 0; wl_ < total_layers; wl_++) {
-      const int l = wl_ % nlayers;
-      for (int t = 0; t < ntiles; t++) {
-        mbar_wait(bar_ready + 8 * t, wl_ & 1);
-        if (t == 0) mbar_wait(bar_full + 8 * (wl_ % STAGES), (wl_ / STAGES) & 1);
-        issue_layer(t, l, wl_);
-      }
-      if (wl_ + STAGES - 1 < total_layers) { if (elect_one()) load_layer(wl_ + STAGES - 1); __syncwarp(); }
-    }
-  } else {
-  int wl = 0;                                                          // global layer counter (barrier phases)
-  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: -, -, MMA done wait, epilogue, barrier
+  int wl = 0;                                                          // global layer counter (ring / barrier phases)
+  long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: weights wait, MMA issue, MMA done, epilogue, barrier
   long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): -, -, search pool, descent, network
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
@@ -320,6 +309,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         if (lane == 0) u = atomicAdd(&s_next[par], 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= UB + UE) break;
+        if (T.dbg && lane == 0) atomicAdd(&s_next[2], 1);                // development check: units started ...
         if (u < UB) {
           // backUp + re-solve of π̄: one (game, ancestor) item per thread
           const int i = u * 32 + lane;
@@ -337,34 +327,39 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           const int gl = (u - UB) * 32 + lane;
           if (gl < count) expand_game1<G, SMALL>(P, g0 + gl, gl, SH, S.training, 0);
         }
+        __syncwarp();
+        if (T.dbg && lane == 0) atomicAdd(&s_next[3], 1);                // ... and finished
       }
-      if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 32 + warp] += clock64() - w_t0;
-      named_bar_sync(1, C::WORKERS);
+      const long long w_d0 = T.dbg ? clock64() - w_t0 : 0;
+      named_bar_sync(1, C::THREADS);
+      if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 32 + warp] += w_d0;
       if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // descent of this rollout; its path nodes are listed as the items of the next pool (parity k)
     SH.lv_cnt = s_lvcnt + (k & 1) * BACKUP_LEVELS;
     const long long w_t1 = T.dbg ? clock64() : 0;                      // development trace: per-warp time in the descent
+    if (T.dbg && has_game && lane == 0 && s_next[2] != s_next[3]) T.dbg[blockIdx.x * 64 + 7] += 1;   // a descent started while a pool unit was still running
     if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr);
-    if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 48 + warp] += clock64() - w_t1;
-    named_bar_sync(1, C::WORKERS);
+    const long long w_d1 = T.dbg ? clock64() - w_t1 : 0;
+    named_bar_sync(1, C::THREADS);
+    if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 48 + warp] += w_d1;
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
-    // A operand of the base layer (decoder, mcts_gpu.jl:202-223): this thread's 32 operand columns of its row, for each tile
+    {
+      // A operand of the base layer (decoder, mcts_gpu.jl:202-223): this thread's operand columns of its row
+      u64 x0 = 0, x1 = 0;
+      const int gl = t * TC_TILE_M + r;
+      if (gl < count) {
+        const u64* st = reinterpret_cast<const u64*>(SH.state + gl);      // left there by this rollout's descent
+        const u64 bp = st[0], bo = st[1];
+        constexpr int VS = G::VS;
+        x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
+        x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
+      }
 #pragma unroll
-    for (int t = 0; t < NT; t++) {
-      if (t < ntiles) {
-        u64 x0 = 0, x1 = 0;
-        const int gl = t * TC_TILE_M + r;
-        if (gl < count) {
-          const u64* st = reinterpret_cast<const u64*>(SH.state + gl);    // left there by this rollout's descent
-          const u64 bp = st[0], bo = st[1];
-          constexpr int VS = G::VS;
-          x0 = (VS < 64) ? (bp | (bo << VS)) : bp;
-          x1 = (VS < 64) ? (bo >> (64 - VS)) : bo;
-        }
-        unsigned char* At = sA + t * TC_A_BYTES;
+      for (int j = 0; j < CPW; j++) {
+        const int cs = csb + j;
         const uint32_t bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -377,55 +372,55 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         }
       }
     }
-    fence_proxy_async();
-    named_bar_sync(1, C::WORKERS);
-    if (C::ISSUE_WARP) {
-      if (threadIdx.x == 0) for (int t = 0; t < ntiles; t++) mbar_arrive(bar_ready + 8 * t);   // the issue warp: base layer of every tile
-    } else {
-      if (warp_u == 0) { mbar_wait(bar_full + 8 * (wl % STAGES), (wl / STAGES) & 1); issue_layer(0, 0, wl); }
-      if (threadIdx.x == 32 && wl + STAGES - 1 < total_layers) load_layer(wl + STAGES - 1);
-    }
-    // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run
-    if (has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
-
-    uint32_t sres[16];                                                 // this thread's residual values (swapped orientation)
-    for (int l = 0; l < nlayers; l++, wl++) {
-      const bool is_head = (l == nlayers - 1);
-      const bool ltr = T.dbg != nullptr && threadIdx.x == 0 && !is_head;
-      for (int t = 0; t < ntiles; t++) {
-        unsigned char* At = sA + t * TC_A_BYTES;
-        const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
-        const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
-        long long lt2 = 0, lt3 = 0, lt4 = 0;
-        if (ltr && t == 0) lt2 = clock64();
-        mbar_wait(bar_done + 8 * t, wl & 1);
+    if (t < ntiles) {                                                  // an idle tile rejoins at the end-of-rollout barrier
+      fence_proxy_async();
+      named_bar_sync(2 + t, 32 * WPT);
+      uint32_t sres[16];                                               // this thread's residual values (swapped orientation)
+      for (int l = 0; l < nlayers; l++) {
+        const int wll = wl + l;
+        const int s = wll % STAGES;
+        const bool is_head = (l == nlayers - 1);
+        long long lt0 = 0, lt1 = 0, lt2 = 0;
+        const bool ltr = T.dbg != nullptr && threadIdx.x == 0 && !is_head;
+        if (ltr) lt0 = clock64();
+        if (issuer_warp) {
+          mbar_wait(bar_full + 8 * s, (wll / STAGES) & 1);
+          if (ltr) lt1 = clock64();
+          if (wll == 0 && t_u == 1) mbar_wait(bar_stagger, 0);          // tile 1 trails tile 0 by one MMA phase
+          issue_layer(t_u, l, wll);
+          if (wll == 0 && t_u == 0 && elect_one()) umma_commit(bar_stagger);
+          __syncwarp();
+          if (ltr) lt2 = clock64();
+        }
+        // the weights STAGES - 1 layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the
+        // issuer the request sat on the critical path: 2 k cycles per rollout)
+        if (threadIdx.x == 32 && wll + STAGES - 1 < total_layers) load_layer(wll + STAGES - 1);
+        // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run (the game threads all belong to tile 0)
+        if (l == 0 && has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
+        mbar_wait(bar_done + 8 * t, wll & 1);
         tc_fence_after();
-        if (ltr && t == 0) { lt3 = clock64(); t_ly[2] += lt3 - lt2; }
+        long long lt3 = 0;
+        if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
         if (!is_head) {
           if (SMALL && swapped) {
-            if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, cs, lane, l, At, sres);
-            else epilogue_swapped<FMT, 16>(tmem_acc, wq, cs, lane, l, At, sres);
+            if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, l, At, sres);
+            else epilogue_swapped<FMT, 16>(tmem_acc, wq, csb, lane, l, At, sres);
           } else {
-            epilogue_ordinary<FMT>(tmem_acc, tmem_res, wq, cs, lane, l, l + 2 < nlayers, At);   // the last trunk layer's residual is not read again
+#pragma unroll
+            for (int j = 0; j < CPW; j++) epilogue_ordinary<FMT>(tmem_acc, tmem_res, wq, csb + j, lane, l, l + 2 < nlayers, At);   // the last trunk layer's residual is not read again
           }
           tc_fence_before();
           fence_proxy_async();
-          if (ltr && t == 0) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
-          named_bar_sync(1, C::WORKERS);                               // every warp has written its part of the next A operand of tile t
-          if (C::ISSUE_WARP) {
-            if (threadIdx.x == 0) mbar_arrive(bar_ready + 8 * t);      // next layer of tile t: its MMAs run under the epilogue of the other tile
-          } else {
-            if (warp_u == 0) { mbar_wait(bar_full + 8 * ((wl + 1) % STAGES), ((wl + 1) / STAGES) & 1); issue_layer(0, l + 1, wl + 1); }
-            if (threadIdx.x == 32 && wl + STAGES < total_layers) load_layer(wl + STAGES);
-          }
-          if (ltr && t == 0) t_ly[4] += clock64() - lt4;
+          long long lt4 = 0;
+          if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
+          named_bar_sync(2 + t, 32 * WPT);
+          if (ltr) t_ly[4] += clock64() - lt4;
         } else {
           // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> shared memory (read by the next search phase)
-          const int gl = t * TC_TILE_M + r;
-          const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
+          const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(csb * 32);
 #pragma unroll
           for (int i = 0; i < 2; i++) {
-            const int a0 = cs * 32 + i * 16;
+            const int a0 = csb * 32 + i * 16;                            // NH <= 32: only a warp's first slice can hold head columns
             if (a0 < T.NH) {                                            // warp-uniform
               uint32_t v[16];
               tmem_ld16(tmem_acc + lane_sel + 16 * i, v);
@@ -437,6 +432,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
 #pragma unroll
                 for (int e = 0; e < 16; e++) if (a0 + e == T.A) z[e] = c_sigmoidf(z[e]);
               }
+              const int gl = t * TC_TILE_M + r;
               if (gl < count) {
                 float* so = SH.out + t * SH.out_tile_stride + r * Lay::OUTS;
                 float* o = P.nn_out + (size_t)(g0 + gl) * Lay::OUTS;
@@ -454,7 +450,8 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         }
       }
     }
-    named_bar_sync(1, C::WORKERS);                                     // the outputs are visible to the search phase
+    wl += nlayers;
+    named_bar_sync(1, C::THREADS);                                     // the outputs are visible to the search phase
     if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
   if (T.dbg && threadIdx.x == 0) {
@@ -467,14 +464,13 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   {
     const int sg = threadIdx.x / W, sl = threadIdx.x & (W - 1);
     const unsigned gm = group_mask<W>();
-    constexpr int GROUPS = C::WORKERS / W;
+    constexpr int GROUPS = C::THREADS / W;
 #pragma unroll 1
     for (int p = 0; p * GROUPS < count; p++) {
       const int gl = p * GROUPS + sg;
       if (gl < count) expand_backup_game<G, false>(P, g0 + gl, sl, gm, S.training, 1, nullptr, nullptr, S.cpuct);
     }
   }
-  }   // workers
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();

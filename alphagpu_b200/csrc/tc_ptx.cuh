@@ -46,7 +46,9 @@ AG_D void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.clust
 AG_D void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 AG_D void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 AG_D void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-AG_D void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// bar.sync is an .aligned barrier: every thread of the warp must execute it together (a warp that reaches it diverged would be counted once
+// per fragment), and the compiler does not know that about inline assembly — hence the explicit reconvergence.
+AG_D void named_bar_sync(int id, int nthreads) { __syncwarp(); asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 AG_D void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");

@@ -29,6 +29,7 @@ for L in [int(x) for x in sys.argv[1:]] or [32768, 8192, 1024, 128]:
         print(f"      thread 0: backup item load+update {x[0]/x[2]:.0f} cyc, solve {x[1]/x[2]:.0f} cyc ({x[2]/len(t)/64:.2f} items/rollout); "
               f"select total {x[4]/len(t)/64:.0f} cyc at warp-max depth, own depth {x[5]/len(t)/64:.2f}, first level {x[6]/len(t)/64:.0f} cyc; "
               f"newton loop {x[3]/x[2]:.0f} cyc; select level 0: loads {x[8]/len(t)/64:.0f}, +philox {x[9]/len(t)/64:.0f}, +scan {x[10]/len(t)/64:.0f}; philox alone {x[11]/len(t)/64:.0f}, entry->philox {x[12]/len(t)/64:.0f}")
+    print("      descents that started while a pool unit was still running (must be 0):", int(t[:, 7].sum()))
     pw, dw = t[:, 32:48].mean(0) / 63, t[:, 48:64].mean(0) / 64
     print("      per-warp busy cycles in the search pool:", " ".join(f"{x:.0f}" for x in pw), f"(max {pw.max():.0f})")
     print("      per-warp cycles in the descent:", " ".join(f"{x:.0f}" for x in dw), f"(max {dw.max():.0f})")
