@@ -38,7 +38,10 @@ template <class G, int NT> struct FCfg {
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
   static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
-  static constexpr int TMEM_COLS = 256 * NT;                           // accumulators + fp32 residual stream
+  // tensor memory: NT x 128 accumulator columns + NT x 128 columns of fp32 residual stream; the small-batch kernel takes all 512 columns
+  // and, in the swapped orientation, keeps the trunk weights — the A operand there — resident in columns 64..511 (TW_COL0 + 64 per layer)
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int TW_COL0 = 64, TW_MAX_LAYERS = 7;
   static_assert(SMEM <= 227 * 1024, "shared memory per CTA");
 };
 
@@ -138,6 +141,9 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   // The weight image (out x in, K-major) serves as the A operand unchanged and the activation tile as the B operand unchanged.
   const bool swapped = SMALL && count <= 64;                           // CTA-uniform; 65..128 games keep the ordinary orientation
   const int NS = count <= 32 ? 32 : 64;
+  // ... and then the weights are the A operand: resident in tensor memory for the whole ply (tcgen05.mma with A from TMEM) when the trunk
+  // fits its 448 spare columns, instead of streamed through shared memory for every rollout
+  const bool ts_mode = swapped && T.nlayers - 1 <= C::TW_MAX_LAYERS;
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -219,6 +225,28 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   const uint32_t tmem_base_u = __shfl_sync(0xffffffffu, tmem_base, 0);
   const uint32_t one = (FMT == 0) ? 0x3F80u : 0x3C00u;
 
+  if (ts_mode) {
+    // trunk weights -> tensor memory.  Layer l lives in columns TW_COL0 + 64 l .. + 63: out-feature (row) m in lane m, the 128 inputs packed
+    // two per column.  The global image is the shared-memory operand image (K-major, 128B-swizzled, two 64-input tiles of 128 rows x
+    // 128 bytes): this thread un-swizzles row 32 wq + lane of the layers l = warp / 4, warp / 4 + 4.
+    for (int l = warp >> 2; l < nlayers - 1; l += 4) {
+      const unsigned char* img = T.img + (size_t)l * TC_W_STAGE_BYTES;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {                                    // 16 columns = 32 inputs = 4 chunks of 16 bytes
+        uint32_t v[16];
+#pragma unroll
+        for (int c4 = 0; c4 < 4; c4++) {
+          const int c = (q & 1) * 4 + c4;                              // chunk within the 64-input tile q >> 1
+          const uint4 x = *reinterpret_cast<const uint4*>(img + (q >> 1) * TC_KTILE_BYTES_A + r * 128 + ((c ^ (r & 7)) << 4));
+          v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
+        }
+        tmem_st16(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(C::TW_COL0 + 64 * l + 16 * q), v);
+      }
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+
   // one thread per game for the descent: the game's uid and node count stay in its registers for the whole ply; the root's state and the
   // first Philox block of the coming descent wait in shared memory
   const bool has_game = (int)threadIdx.x < count;
@@ -247,7 +275,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
 
   // issue of one layer's MMAs for tile t (called by the issuer warp only, all lanes, warp-uniform arguments)
   auto issue_layer = [&](const int t, const int l, const int wl_) {
-    const int s = wl_ % STAGES;
+    const int s = ts_mode ? 0 : wl_ % STAGES;
     const bool is_head = (l == nlayers - 1);
     const int nl = is_head ? T.NH : TC_N;
     tc_fence_after();
@@ -256,7 +284,15 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
       const uint64_t ad0 = umma_desc(smem_u32(sA) + (uint32_t)(t * TC_A_BYTES));
       const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * TC_W_STAGE_BYTES));
       const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
-      if (SMALL && swapped && !is_head) {
+      if (SMALL && ts_mode && !is_head) {
+        const uint32_t idesc = umma_idesc<FMT>(NS);                     // M = 128 out-features, N = NS games
+        const uint32_t tw = tmem_base_u + (uint32_t)(C::TW_COL0 + 64 * l);
+#pragma unroll
+        for (int ks = 0; ks < TC_N / 16; ks++) {
+          const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
+          umma_ts(tmem_acc_u, tw + (uint32_t)(8 * ks), ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights (TMEM) as A, activations as B
+        }
+      } else if (SMALL && swapped && !is_head) {
         const uint32_t idesc = umma_idesc<FMT>(NS);                     // M = 128 out-features, N = NS games
 #pragma unroll
         for (int ks = 0; ks < TC_N / 16; ks++) {
@@ -279,8 +315,14 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     __syncwarp();
   };
 
-  if (threadIdx.x == 32) {                                             // fill the ring: STAGES - 1 layers ahead
-    for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
+  if (threadIdx.x == 32) {
+    if (ts_mode) {                                                     // only the head layer is read from shared memory: loaded once, stage 0
+      const uint32_t bytes = (uint32_t)(T.NH * TC_N * 2);
+      mbar_expect_tx(bar_full, bytes);
+      bulk_g2s(smem_u32(sW), T.img + (size_t)(nlayers - 1) * TC_W_STAGE_BYTES, bytes, bar_full);
+    } else {                                                           // fill the ring: STAGES - 1 layers ahead
+      for (int i = 0; i < STAGES - 1 && i < total_layers; i++) load_layer(i);
+    }
   }
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
   long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: weights wait, MMA issue, MMA done, epilogue, barrier
@@ -384,7 +426,8 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         const bool ltr = T.dbg != nullptr && threadIdx.x == 0 && !is_head;
         if (ltr) lt0 = clock64();
         if (issuer_warp) {
-          mbar_wait(bar_full + 8 * s, (wll / STAGES) & 1);
+          if (!ts_mode) mbar_wait(bar_full + 8 * s, (wll / STAGES) & 1);
+          else if (is_head) mbar_wait(bar_full, 0);                      // the resident head image (complete after the first wait)
           if (ltr) lt1 = clock64();
           if (wll == 0 && t_u == 1) mbar_wait(bar_stagger, 0);          // tile 1 trails tile 0 by one MMA phase
           issue_layer(t_u, l, wll);
@@ -394,7 +437,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         }
         // the weights STAGES - 1 layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the
         // issuer the request sat on the critical path: 2 k cycles per rollout)
-        if (threadIdx.x == 32 && wll + STAGES - 1 < total_layers) load_layer(wll + STAGES - 1);
+        if (!ts_mode && threadIdx.x == 32 && wll + STAGES - 1 < total_layers) load_layer(wll + STAGES - 1);
         // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run (the game threads all belong to tile 0)
         if (l == 0 && has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
         mbar_wait(bar_done + 8 * t, wll & 1);

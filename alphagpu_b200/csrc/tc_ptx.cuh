@@ -66,6 +66,16 @@ AG_D void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t id
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand (M x K, K-major: row m in TMEM lane m, K elements packed two per 32-bit column) is read
+// from tensor memory instead of shared memory — an SS-mode MMA with a small N is bound by the shared-memory read of its 4 KB A operand
+AG_D void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // one lane of a converged warp (issue tcgen05.mma from a warp-UNIFORM branch and elect inside it: from a divergent `lane == 0` branch
 // every operand goes through an ELECT / R2UR / BRA.U.ANY waterfall, ~75 cycles per instruction)
 AG_D bool elect_one() {
