@@ -25,6 +25,12 @@ namespace ag {
 namespace fused {
 using namespace tc;
 
+// -DAG_TRACE=1 builds the development library whose per-ply kernel records clock64 phase traces into the buffer set by
+// agpu_debug_tc_trace (scripts/fused_trace.py); the product library contains none of that code.
+#ifndef AG_TRACE
+#define AG_TRACE 0
+#endif
+
 // NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
@@ -34,7 +40,7 @@ template <class G, int NT> struct FCfg {
   static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
-  static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * BACKUP_LEVELS + 1 + 2 * PATH_SMEM_DEPTH;
+  static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * ITEMS_PER_GAME + 2 + 2 * PATH_SMEM_DEPTH;
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
   static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
@@ -153,9 +159,9 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile, [8] stagger (one-shot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   int* s_next = reinterpret_cast<int*>(bars + 17);                     // [2] work-unit counters of the search pool, by rollout parity (+ [2] development)
-  int* s_lvcnt = reinterpret_cast<int*>(bars + 19);                    // [2][BACKUP_LEVELS] items per level, by rollout parity
-  float* sbias = reinterpret_cast<float*>(bars + 19) + 2 * BACKUP_LEVELS;   // [128] head biases
-  static_assert(19 * 8 + 2 * BACKUP_LEVELS * 4 + TC_N * 4 <= 1024, "fixed part of the work area");
+  int* s_lvcnt = reinterpret_cast<int*>(bars + 19);                    // [2] items listed by the last descent, by rollout parity
+  float* sbias = reinterpret_cast<float*>(bars + 20);                  // [128] head biases
+  static_assert(20 * 8 + TC_N * 4 <= 1024, "fixed part of the work area");
   // hand-off between the phases of a rollout (search.cuh: RolloutShared)
   RolloutShared<G> SH;
   SH.state = reinterpret_cast<State*>(reinterpret_cast<unsigned char*>(bars) + 1024);      // 16-byte aligned
@@ -164,10 +170,11 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   SH.hdr = reinterpret_cast<NodeHdr*>(SH.rnd + C::GAMES);
   SH.d = reinterpret_cast<int*>(SH.hdr + C::GAMES);
   SH.lv_item = reinterpret_cast<uint16_t*>(SH.d + C::GAMES);
-  SH.lv_stride = C::GAMES;
+  SH.lv_cap = ITEMS_PER_GAME * C::GAMES;
   SH.lv_cnt = s_lvcnt;
-  SH.leaf = reinterpret_cast<uint8_t*>(SH.lv_item + BACKUP_LEVELS * C::GAMES);
-  SH.pn = SH.leaf + C::GAMES;
+  SH.leaf = reinterpret_cast<uint8_t*>(SH.lv_item + ITEMS_PER_GAME * C::GAMES);
+  SH.ovf = SH.leaf + C::GAMES;
+  SH.pn = SH.ovf + C::GAMES;
   SH.pm = SH.pn + C::GAMES * PATH_SMEM_DEPTH;
   static_assert(sizeof(State) % 8 == 0 && sizeof(Philox4) == 16 && sizeof(NodeHdr) == 8, "hand-off layout");
   // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
@@ -180,6 +187,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   SH.nc_nodes = SMALL ? min(P.R, C::TREE_BYTES / (CacheSlot<Lay::APAD>::BYTES * count)) : 0;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dbg_on = AG_TRACE && T.dbg != nullptr;
   const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 3), bar_done = smem_u32(bars + 6), bar_stagger = smem_u32(bars + 8);
 
   if (threadIdx.x == 0) {
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     mbar_init(bar_stagger, 1);
     fence_barrier_init();
     s_next[0] = s_next[1] = s_next[2] = s_next[3] = 0;
-    for (int i = 0; i < 2 * BACKUP_LEVELS; i++) s_lvcnt[i] = 0;
+    s_lvcnt[0] = s_lvcnt[1] = 0;
   }
   if (threadIdx.x < TC_N) sbias[threadIdx.x] = T.bias[threadIdx.x];
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), C::TMEM_COLS);        // NT x 128 accumulator columns + NT x 128 residual columns
@@ -258,6 +266,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     SH.root[threadIdx.x] = *reinterpret_cast<const State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
     SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
     SH.d[threadIdx.x] = 0;
+    SH.ovf[threadIdx.x] = 0;
     if (SMALL) {
       // fill the node cache with the nodes that exist when the ply starts (the root alone after root_reset); read back only by this thread
       typedef CacheSlot<Lay::APAD> CS;
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   }
   int wl = 0;                                                          // global layer counter (ring / barrier phases)
   long long t_ly[5] = {0, 0, 0, 0, 0};                                  // development trace of thread 0: weights wait, MMA issue, MMA done, epilogue, barrier
-  long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = T.dbg ? clock64() : 0;   // development trace (agpu_debug_tc_trace): -, -, search pool, descent, network
+  long long t_ph[5] = {0, 0, 0, 0, 0}, t_mark = dbg_on ? clock64() : 0;   // development trace (agpu_debug_tc_trace): -, -, search pool, descent, network
   for (int k = 0; k < visits; k++) {
     const int last = (k == visits - 1);
     // ================= search phase =================
@@ -336,32 +345,24 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
       // expansion of that game's leaf touch different nodes, and both only read what the network and the descent left in shared memory,
       // so the units are independent.
       const int par = (k - 1) & 1;
-      const int* cnt = s_lvcnt + par * BACKUP_LEVELS;
-      if (threadIdx.x == 0) {                                          // counters of the other parity: for the coming descent / the next pool
-        s_next[par ^ 1] = 0;
-        for (int lv = 0; lv < BACKUP_LEVELS; lv++) s_lvcnt[(par ^ 1) * BACKUP_LEVELS + lv] = 0;
-      }
-      const long long w_t0 = T.dbg ? clock64() : 0;                    // development trace: per-warp busy time in the pool
-      int n_items = 0;
-#pragma unroll
-      for (int lv = 0; lv < BACKUP_LEVELS; lv++) n_items += cnt[lv];
+      if (threadIdx.x == 0) { s_next[par ^ 1] = 0; s_lvcnt[par ^ 1] = 0; }   // counters of the other parity: for the coming descent / the next pool
+      const long long w_t0 = dbg_on ? clock64() : 0;                   // development trace: per-warp busy time in the pool
+      const int n_items = min(s_lvcnt[par], SH.lv_cap);
       const int UB = (n_items + 31) >> 5, UE = (count + 31) >> 5;
       while (true) {
         int u = 0;
         if (lane == 0) u = atomicAdd(&s_next[par], 1);
         u = __shfl_sync(0xffffffffu, u, 0);
         if (u >= UB + UE) break;
-        if (T.dbg && lane == 0) atomicAdd(&s_next[2], 1);                // development check: units started ...
+        if (dbg_on && lane == 0) atomicAdd(&s_next[2], 1);                // development check: units started ...
         if (u < UB) {
           // backUp + re-solve of π̄: one (game, ancestor) item per thread
           const int i = u * 32 + lane;
           if (i < n_items) {
-            int lv = 0, base = 0;
-            while (lv < BACKUP_LEVELS - 1 && i >= base + cnt[lv]) { base += cnt[lv]; lv++; }
-            const int item = SH.lv_item[lv * C::GAMES + (i - base)];
+            const int item = SH.lv_item[i];
             const int gl = item & 0xFF, jj = item >> 8;
             const LeafEval E = leaf_eval1<G>(SH, gl);
-            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr,
+            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr,
                            SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
                            SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
           }
@@ -370,22 +371,29 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           if (gl < count) expand_game1<G, SMALL>(P, g0 + gl, gl, SH, S.training, 0);
         }
         __syncwarp();
-        if (T.dbg && lane == 0) atomicAdd(&s_next[3], 1);                // ... and finished
+        if (dbg_on && lane == 0) atomicAdd(&s_next[3], 1);                // ... and finished
       }
-      const long long w_d0 = T.dbg ? clock64() - w_t0 : 0;
+      if (has_game && SH.ovf[threadIdx.x] < SH.d[threadIdx.x]) {       // the list was full: this game backs up the rest of its path itself
+        const int gl = (int)threadIdx.x;
+        const LeafEval E = leaf_eval1<G>(SH, gl);
+        for (int jj = SH.ovf[gl]; jj < SH.d[gl]; jj++)
+          backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, nullptr, SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
+                         SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
+      }
+      const long long w_d0 = dbg_on ? clock64() - w_t0 : 0;
       named_bar_sync(1, C::THREADS);
-      if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 32 + warp] += w_d0;
-      if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
+      if (dbg_on && lane == 0) T.dbg[blockIdx.x * 64 + 32 + warp] += w_d0;
+      if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // descent of this rollout; its path nodes are listed as the items of the next pool (parity k)
-    SH.lv_cnt = s_lvcnt + (k & 1) * BACKUP_LEVELS;
-    const long long w_t1 = T.dbg ? clock64() : 0;                      // development trace: per-warp time in the descent
-    if (T.dbg && has_game && lane == 0 && s_next[2] != s_next[3]) T.dbg[blockIdx.x * 64 + 7] += 1;   // a descent started while a pool unit was still running
-    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (T.dbg && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr);
-    const long long w_d1 = T.dbg ? clock64() - w_t1 : 0;
+    SH.lv_cnt = s_lvcnt + (k & 1);
+    const long long w_t1 = dbg_on ? clock64() : 0;                      // development trace: per-warp time in the descent
+    if (dbg_on && has_game && lane == 0 && s_next[2] != s_next[3]) T.dbg[blockIdx.x * 64 + 7] += 1;   // a descent started while a pool unit was still running
+    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr);
+    const long long w_d1 = dbg_on ? clock64() - w_t1 : 0;
     named_bar_sync(1, C::THREADS);
-    if (T.dbg && lane == 0) T.dbg[blockIdx.x * 64 + 48 + warp] += w_d1;
-    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
+    if (dbg_on && lane == 0) T.dbg[blockIdx.x * 64 + 48 + warp] += w_d1;
+    if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
     {
@@ -416,14 +424,14 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     }
     if (t < ntiles) {                                                  // an idle tile rejoins at the end-of-rollout barrier
       fence_proxy_async();
-      named_bar_sync(2 + t, 32 * WPT);
+      named_bar_sync(NT == 1 ? 2 : 2 + t, 32 * WPT);   // (a compile-time barrier id where there is one tile)
       uint32_t sres[16];                                               // this thread's residual values (swapped orientation)
       for (int l = 0; l < nlayers; l++) {
         const int wll = wl + l;
         const int s = wll % STAGES;
         const bool is_head = (l == nlayers - 1);
         long long lt0 = 0, lt1 = 0, lt2 = 0;
-        const bool ltr = T.dbg != nullptr && threadIdx.x == 0 && !is_head;
+        const bool ltr = dbg_on && threadIdx.x == 0 && !is_head;
         if (ltr) lt0 = clock64();
         if (issuer_warp) {
           if (!ts_mode) mbar_wait(bar_full + 8 * s, (wll / STAGES) & 1);
@@ -456,7 +464,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           fence_proxy_async();
           long long lt4 = 0;
           if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
-          named_bar_sync(2 + t, 32 * WPT);
+          named_bar_sync(NT == 1 ? 2 : 2 + t, 32 * WPT);   // (a compile-time barrier id where there is one tile)
           if (ltr) t_ly[4] += clock64() - lt4;
         } else {
           // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> shared memory (read by the next search phase)
@@ -495,9 +503,9 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     }
     wl += nlayers;
     named_bar_sync(1, C::THREADS);                                     // the outputs are visible to the search phase
-    if (T.dbg && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
+    if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
-  if (T.dbg && threadIdx.x == 0) {
+  if (dbg_on && threadIdx.x == 0) {
     for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 64 + i] = t_ph[i];
     T.dbg[blockIdx.x * 64 + 5] = count; T.dbg[blockIdx.x * 64 + 6] = visits;
     for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 64 + 24 + i] = t_ly[i];

@@ -119,7 +119,7 @@ constexpr int PATH_SMEM_DEPTH = 16;          // path entries per game held in sh
 AG_D uint2 hot_ld_u2(const void* a) { return *reinterpret_cast<const uint2*>(a); }
 AG_D uint4 hot_ld_u4(const void* a) { return *reinterpret_cast<const uint4*>(a); }
 AG_D float4 hot_ld_f4(const void* a) { return *reinterpret_cast<const float4*>(a); }
-constexpr int BACKUP_LEVELS = 8;             // item lists of the backup phase: levels 0..6 of a path one list each, deeper levels share the last
+constexpr int ITEMS_PER_GAME = 8;            // capacity of the backup phase's item list, per game of the CTA (mean path length: 3-5)
 template <class G>
 struct RolloutShared {
   typename G::State* state;  // [GAMES] state of the leaf
@@ -132,9 +132,10 @@ struct RolloutShared {
   uint8_t* leaf;             // [GAMES]
   uint8_t* pn;               // [GAMES][PATH_SMEM_DEPTH] path nodes
   uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
-  int* lv_cnt;               // [BACKUP_LEVELS] items per level of the last descent (filled by the descents through shared-memory atomics)
-  uint16_t* lv_item;         // [BACKUP_LEVELS][GAMES] item = local game | path index << 8
-  int lv_stride;             // GAMES
+  int* lv_cnt;               // items of the last descent: entries reserved in lv_item (may exceed lv_cap)
+  uint16_t* lv_item;         // [lv_cap] item = local game | path index << 8
+  int lv_cap;                // capacity of the item list
+  uint8_t* ovf;              // [GAMES] number of leading path indices of the game that ARE in the list (== path length unless the list was full)
   unsigned char* nc_base;    // node cache of the small-batch kernel: write-through copy of the descent fields (header, child ids, π̄) of the
   int nc_nodes;              //   first nc_nodes nodes of every game of the CTA; entry (gl, node) at nc_base + (gl * nc_nodes + node) * BYTES
 };
@@ -857,20 +858,24 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   SH.leaf[gl] = (uint8_t)node;
   SH.d[gl] = depth;
   {
-    // The (game, path index) pairs of this descent are the items of the next backup phase: listed level by level, with one shared-memory
-    // atomic per warp and level (the lanes of the warp — gmask — have reconverged here).
+    // The (game, path index) pairs of this descent are the items of the next backup phase.  One list per CTA, filled with one
+    // shared-memory atomic per warp: an inclusive scan of the path lengths over the lanes of the warp (gmask — they have reconverged
+    // here) gives every game its range.  A game whose range does not fit the list keeps its tail for itself: SH.ovf[gl] = first path
+    // index that is not listed, and its own thread backs those up before the barrier of the pool.
     __syncwarp(gmask);
     const int lane = (int)(threadIdx.x & 31);
-    const int maxd = (int)__reduce_max_sync(gmask, (unsigned)depth);
-    for (int lv = 0; lv < maxd; lv++) {
-      const int L = lv < BACKUP_LEVELS ? lv : BACKUP_LEVELS - 1;
-      const unsigned m = __ballot_sync(gmask, depth > lv);
-      const int leader = __ffs((int)m) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(&SH.lv_cnt[L], __popc(m));
-      base = __shfl_sync(gmask, base, leader);
-      if (depth > lv) SH.lv_item[L * SH.lv_stride + base + __popc(m & ((1u << lane) - 1u))] = (uint16_t)(gl | (lv << 8));
-    }
+    int incl = depth;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(gmask, incl, o); if (lane >= o && ((gmask >> (lane - o)) & 1u)) incl += y; }
+    const int top = 31 - __clz((int)gmask);                                           // gmask is a prefix of the warp: its last lane holds the total
+    const int total = __shfl_sync(gmask, incl, top);
+    int base = 0;
+    if (lane == top) base = atomicAdd(SH.lv_cnt, total);
+    base = __shfl_sync(gmask, base, top) + incl - depth;
+    int listed = depth;
+    if (base + depth > SH.lv_cap) listed = base < SH.lv_cap ? SH.lv_cap - base : 0;
+    for (int j = 0; j < listed; j++) SH.lv_item[base + j] = (uint16_t)(gl | (j << 8));
+    SH.ovf[gl] = (uint8_t)listed;
   }
   if (last_rollout) {
     P.leaf[g] = node;                                                                  // :195
