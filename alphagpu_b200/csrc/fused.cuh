@@ -93,32 +93,40 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, int l, u
   }
 }
 
-// Epilogue of a trunk layer in the ordinary orientation: row r = 32*wq + lane of the tile, the 32 columns of slice cs.
+// Epilogue of a trunk layer in the ordinary orientation: row r = 32*wq + lane of the tile, NSL consecutive 32-column slices from cs0.
 // b = relu(acc) (base layer) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b).
-template <int FMT>
-AG_D void epilogue_ordinary(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs, int lane, int l, bool keep, unsigned char* At) {
+// The tensor-memory loads of a 16-column chunk are issued before the previous chunk is processed (tcgen05.wait::ld waits for ALL
+// outstanding loads, so without this the load latency is exposed once per chunk: 4 or 8 times per layer).
+template <int FMT, int NSL>
+AG_D void epilogue_ordinary(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs0, int lane, int l, bool keep, unsigned char* At) {
   const int r = wq * 32 + lane;
-  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * 32);
+  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs0 * 32);
+  constexpr int NCH = 2 * NSL;                                          // 16-column chunks
+  uint32_t va[2][16], vh[2][16];
+  tmem_ld16(tmem_acc + lane_sel, va[0]);
+  if (l > 0) tmem_ld16(tmem_res + lane_sel, vh[0]);
 #pragma unroll
-  for (int i = 0; i < 2; i++) {
-    uint32_t va[16], vh[16];
-    tmem_ld16(tmem_acc + lane_sel + 16 * i, va);
-    if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * i, vh);
-    tmem_ld_wait();
+  for (int i = 0; i < NCH; i++) {
+    const int b = i & 1;
+    tmem_ld_wait();                                                     // chunk i has arrived
+    if (i + 1 < NCH) {                                                  // chunk i + 1 in flight while chunk i is processed
+      tmem_ld16(tmem_acc + lane_sel + 16 * (i + 1), va[b ^ 1]);
+      if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * (i + 1), vh[b ^ 1]);
+    }
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-      const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
-      const float hv = (l == 0) ? ra : __uint_as_float(vh[e]) + ra;
-      vh[e] = __float_as_uint(hv);
+      const float ra = fmaxf(__uint_as_float(va[b][e]), 0.f);
+      const float hv = (l == 0) ? ra : __uint_as_float(vh[b][e]) + ra;
+      vh[b][e] = __float_as_uint(hv);
     }
-    if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh);
+    if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh[b]);
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
-      const int c = 4 * cs + 2 * i + c2;
-      const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[8 * c2 + 0]), __uint_as_float(vh[8 * c2 + 1])),
-                                  pack2<FMT>(__uint_as_float(vh[8 * c2 + 2]), __uint_as_float(vh[8 * c2 + 3])),
-                                  pack2<FMT>(__uint_as_float(vh[8 * c2 + 4]), __uint_as_float(vh[8 * c2 + 5])),
-                                  pack2<FMT>(__uint_as_float(vh[8 * c2 + 6]), __uint_as_float(vh[8 * c2 + 7])));
+      const int c = 4 * cs0 + 2 * i + c2;
+      const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 0]), __uint_as_float(vh[b][8 * c2 + 1])),
+                                  pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 2]), __uint_as_float(vh[b][8 * c2 + 3])),
+                                  pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 4]), __uint_as_float(vh[b][8 * c2 + 5])),
+                                  pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 6]), __uint_as_float(vh[b][8 * c2 + 7])));
       *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
     }
   }
@@ -457,8 +465,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
             if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, l, At, sres);
             else epilogue_swapped<FMT, 16>(tmem_acc, wq, csb, lane, l, At, sres);
           } else {
-#pragma unroll
-            for (int j = 0; j < CPW; j++) epilogue_ordinary<FMT>(tmem_acc, tmem_res, wq, csb + j, lane, l, l + 2 < nlayers, At);   // the last trunk layer's residual is not read again
+            epilogue_ordinary<FMT, CPW>(tmem_acc, tmem_res, wq, csb, lane, l, l + 2 < nlayers, At);   // the last trunk layer's residual is not read again
           }
           tc_fence_before();
           fence_proxy_async();

@@ -94,6 +94,75 @@ def algorithmic_bytes_per_sim(A, S, dbar):
     return {"select": select, "expand_backup": expand, "nn": nn}
 
 
+# BASELINE.json configs 3-5 (large boards, DenseNet 512x8) at the shard one GPU plays when the configuration's games are spread over the
+# GPUs it names; config 3 names 2/4/8 GPUs: its shard follows the GPU count of this run (a quarter of the games on one GPU).
+EXTRA_CONFIGS = [
+    dict(name="config3_hex7_densenet512x8_rollout64", game=("hex", 7, 0), width=512, blocks=8, rollout=64, total_games=65536, gpus=(2, 4, 8), S=34),
+    dict(name="config4_gobang9_densenet512x8_rollout128", game=("gobang", 9, 5), width=512, blocks=8, rollout=128, total_games=131072, gpus=(8,), S=50),
+    dict(name="config5_reversi8_densenet512x8_rollout64", game=("reversi8", 0, 0), width=512, blocks=8, rollout=64, total_games=262144, gpus=(8,), S=26),
+]
+
+
+def run_extra_config(cfg, ag, torch, parallel, rank, world, local_rank, nn_mode, sync, peaks_):
+    """One generation of self-play of a large-board configuration at its per-GPU shard: device-timed value, end-to-end value with host
+    buffers (weights H2D, samples D2H inside the timed region), rooflines of the search kernels (HBM) and of the tcgen05 chain (tensor)."""
+    import numpy as np
+    spec = ag.GameSpec.named(*cfg["game"])
+    ngpu = world if world in cfg["gpus"] else (4 if len(cfg["gpus"]) > 1 else cfg["gpus"][0])
+    games = cfg["total_games"] // ngpu
+    R, n, k = cfg["rollout"], cfg["width"], cfg["blocks"]
+    net = ag.ressimplesf(2 * spec.VectorizedState, spec.maxActions, n, k, seed=0)
+    ctx = ag.Context(spec, R, games, n, k, device=local_rank, nn_mode=nn_mode)
+    ctx.set_weights(net)
+    uid_base = rank * games
+    ctx.selfplay(R, games, cpuct=CPUCT, seed=100, uid_base=uid_base, want_samples=False)              # warm-up
+    sync()
+    res, st, _ = ctx.selfplay(R, games, cpuct=CPUCT, seed=0, uid_base=uid_base, want_samples=False)
+    assert st["faults"] == 0 and int(res.sum()) == games
+    cap = games * spec.maxLengthGame
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
+    bufs = dict(state=pin((cap, 2 * spec.VectorizedState), torch.int8), policy=pin((cap, spec.maxActions), torch.float32), player=pin((cap,), torch.int8),
+                value=pin((cap,), torch.float32), fstate=pin((cap, spec.FeatureSize), torch.int8), game=pin((cap,), torch.int32), ply=pin((cap,), torch.int32))
+    sync()
+    t0 = time.perf_counter()
+    ctx.set_weights(net)
+    _, est, smp = ctx.selfplay(R, games, cpuct=CPUCT, seed=0, uid_base=uid_base, out=bufs)
+    sync()
+    e2e_wall = time.perf_counter() - t0
+    d2h = sum(v.nbytes for v in smp.values()) + 24
+    ctx.profile(True)
+    ctx.kernel_times(reset=True)
+    _, pst, _ = ctx.selfplay(R, games, cpuct=CPUCT, seed=0, uid_base=uid_base, want_samples=False)
+    kt = ctx.kernel_times()
+    ctx.close()
+    del bufs
+    (dev_ms, e2e_wall), (sims, e2e_sims, positions) = parallel.reduce_max_sum([st["device_ms"], e2e_wall], [st["sims"], est["sims"], st["positions"]],
+                                                                               device="cuda" if world > 1 else None)
+    hbm, tflops, peak_src = peaks_
+    A = spec.maxActions
+    dbar = kt["nodes_traversed"] / max(1, kt["descents"])
+    per_sim = algorithmic_bytes_per_sim(A, cfg["S"], dbar)
+    classes = {kk: v for kk, v in kt.items() if isinstance(v, dict) and v["launches"]}
+    total_ms = sum(v["ms"] for v in classes.values())
+    search_ms = sum(classes.get(c, {"ms": 0.0})["ms"] for c in ("select", "expand_backup"))
+    nn_ms = classes.get("nn", {"ms": 0.0})["ms"]
+    f_sim = 2 * (2 * spec.VectorizedState * n + k * n * n + n * (A + 1))
+    out = {"name": cfg["name"], "games_per_gpu": games, "as_if_gpus": ngpu, "rollouts": R, "value": sims / (dev_ms * 1e-3), "unit": "sims/s", "ms_per_generation": dev_ms,
+           "positions_per_sec": positions / (dev_ms * 1e-3), "d_bar": dbar,
+           "e2e": {"value": e2e_sims / e2e_wall, "unit": "sims/s", "h2d_bytes_per_step": net.nbytes, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall},
+           "kernel_ms": {kk: round(v["ms"], 3) for kk, v in classes.items()}}
+    if search_ms > 0:
+        bytes_sim = per_sim["select"] + per_sim["expand_backup"]
+        ach = bytes_sim * pst["sims"] / (search_ms * 1e-3) / 1e9
+        out["roofline"] = {"kernel": "search kernels (step = expand + backUp + descent)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                           "traffic": None, "peak_source": peak_src, "bytes_per_sim": bytes_sim, "share_of_step": search_ms / total_ms}
+    if nn_ms > 0:
+        tf = f_sim * pst["sims"] / (nn_ms * 1e-3) / 1e12
+        out["roofline_nn"] = {"kernel": "tc_mlp512 (tcgen05 chain)", "bound": "tensor", "achieved": tf, "peak": tflops, "unit": "TFLOP/s", "frac": tf / tflops,
+                              "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms}
+    return out
+
+
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle port of mcts_gpu.jl, all host threads), bounded sample per step."""
     if rank != 0:
@@ -135,6 +204,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nn-mode", type=int, default=2, help="2 = fp16 tcgen05 chain (default), 0 = bf16 tcgen05 chain, 1 = fp32 CUDA cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip configs 3-5, strong scaling and the gathered generation")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -215,7 +285,45 @@ def main():
     kt = ctx.kernel_times()
     ctx.profile(False)
     lay = ctx.layout()
+
+    # ---- extras (never allowed to break the headline line) ----
+    from alphagpu_b200 import parallel
+    strong, gen_e2e, extra_configs = None, None, []
+    if not args.no_extras:
+        try:
+            # strong scaling: the 32768 games of the metric split over the ranks (uids rank*G/N ...), time = max over ranks
+            gl = GAMES // world
+            ctx.selfplay(ROLLOUT, gl, cpuct=CPUCT, seed=55, uid_base=rank * gl, want_samples=False)
+            sync()
+            _, sst, _ = ctx.selfplay(ROLLOUT, gl, cpuct=CPUCT, seed=0, uid_base=rank * gl, want_samples=False)
+            (sms,), (ssims,) = parallel.reduce_max_sum([sst["device_ms"]], [sst["sims"]], device="cuda" if world > 1 else None)
+            strong = {"workload": WORKLOAD, "total_games": GAMES, "games_per_gpu": gl, "value": ssims / (sms * 1e-3), "unit": "sims/s", "ms_per_generation": sms,
+                      "scaling": "strong"}
+            # one generation end to end INCLUDING the sample gather over the ranks (NCCL all_gather of the padded blocks when world > 1)
+            sync()
+            t0g = time.perf_counter()
+            ctx.set_weights(net)
+            _, gst, gsmp = ctx.selfplay(ROLLOUT, gl, cpuct=CPUCT, seed=0, uid_base=rank * gl, out=bufs)
+            t1g = time.perf_counter()
+            gathered = parallel.gather_samples({kk: gsmp[kk] for kk in ("state", "policy", "player", "value", "fstate")}, device="cuda" if world > 1 else None)
+            sync()
+            t2g = time.perf_counter()
+            (gwall, ggather), (gsims,) = parallel.reduce_max_sum([t2g - t0g, t2g - t1g], [gst["sims"]], device="cuda" if world > 1 else None)
+            gen_e2e = {"workload": WORKLOAD, "total_games": GAMES, "value": gsims / gwall, "unit": "sims/s", "ms_per_step": 1e3 * gwall, "gather_ms": 1e3 * ggather,
+                       "gathered_samples": int(len(gathered["player"])), "gather": "nccl all_gather of padded per-rank blocks" if world > 1 else "single rank: none"}
+        except Exception as e:                                                   # pragma: no cover
+            stage(f"strong-scaling / gather leg failed: {e!r}")
+            strong = strong or {"error": repr(e)}
     ctx.close()
+    del bufs
+    if not args.no_extras:
+        for cfg in EXTRA_CONFIGS:
+            try:
+                extra_configs.append(run_extra_config(cfg, ag, torch, parallel, rank, world, local_rank, args.nn_mode, sync, peaks()))
+                stage(f"extra config {cfg['name']} done")
+            except Exception as e:                                               # pragma: no cover
+                stage(f"extra config {cfg['name']} failed: {e!r}")
+                extra_configs.append({"name": cfg["name"], "error": repr(e)})
 
     stage("search legs done")
     # ---- the training step that follows a generation (train.jl): batch 8192 (main4IARow.jl:102-105) split over the ranks,
@@ -254,7 +362,6 @@ def main():
         train_info = {"error": repr(e)}
 
     # ---- reduce over ranks: time = max, work = sum ----
-    from alphagpu_b200 import parallel
     (dev_ms, wall, e2e_wall), w = parallel.reduce_max_sum([dev_ms, wall, e2e_wall], [sims, positions, launches, e2e_sims, d2h, h2d],
                                                           device="cuda" if world > 1 else None)
     sims, positions, launches, e2e_sims, d2h, h2d = [int(x) for x in w]
@@ -314,6 +421,9 @@ def main():
         "roofline_nn": {"kernel": nn_name, "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
                         "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
+        "strong_scaling": strong,
+        "generation_e2e": gen_e2e,
+        "extra_configs": extra_configs,
         "train_step": train_info,
     }
 
