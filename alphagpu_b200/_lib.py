@@ -79,6 +79,14 @@ SIGNATURES = {
     "agpu_get_tree": (C.c_int, [_VP, _I64, C.POINTER(TreeDump)]),
     "agpu_selfplay": (C.c_int, [_VP, _I32, _I32, _I64, _U32, _F, _F, _U64, C.POINTER(Samples), _VP, C.POINTER(RunStats)]),
     "agpu_duel": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _U32, _F, _U64, _VP, C.POINTER(RunStats)]),
+    "agpu_multi_create": (C.c_int, [C.POINTER(_VP), C.POINTER(Config), _I32, _VP]),
+    "agpu_multi_destroy": (None, [_VP]),
+    "agpu_multi_last_error": (C.c_char_p, [_VP]),
+    "agpu_multi_ngpus": (C.c_int, [_VP]),
+    "agpu_multi_context": (_VP, [_VP, _I32]),
+    "agpu_multi_set_weights": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "agpu_multi_selfplay": (C.c_int, [_VP, _I32, _I32, _I64, _U32, _F, _F, _U64, C.POINTER(Samples), _VP, C.POINTER(RunStats)]),
+    "agpu_multi_duel": (C.c_int, [_VP, _I32, _I32, _I32, _I64, _U32, _F, _U64, _VP, C.POINTER(RunStats)]),
     "agpu_profile": (C.c_int, [_VP, _I32]),
     "agpu_get_kernel_times": (C.c_int, [_VP, C.POINTER(KernelTimes), _I32]),
     "agpu_layout_info": (C.c_int, [_VP, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),

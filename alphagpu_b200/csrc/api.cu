@@ -1,5 +1,7 @@
 // api.cu — the C ABI of include/alphagpu.h: argument checking and run-time dispatch on the game plugin.
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "engine.cuh"
 
@@ -55,6 +57,71 @@ static bool fill_info(int32_t game, int32_t n, int32_t nvict, agpu_game_info* o)
     case AGPU_REVERSI6: *o = {37, 36, 36, 50, 152}; return true;                                   // Reversi6x6.jl:6-9
   }
   return false;
+}
+
+// ---- several GPUs behind ONE call from ONE caller thread (the caller is selfplay.jl:34 / :56) ----
+struct agpu_multi {
+  std::vector<agpu_ctx*> ctx;
+  std::string err;
+};
+
+// games [0, n) block-partitioned over `parts` shards: shard r plays [base, base + count)
+static void shard_block(int64_t n, int parts, int r, int64_t* base, int64_t* count) {
+  const int64_t q = n / parts, rem = n % parts;
+  *count = q + (r < rem ? 1 : 0);
+  *base = r * q + (r < rem ? r : rem);
+}
+
+// one host thread per device runs f(r); returns the first non-OK status (AGPU_ERR_ILLEGAL_MOVE ranks last: the run itself completed)
+template <class F> static int multi_for_each(agpu_multi* m, F&& f) {
+  const int n = (int)m->ctx.size();
+  std::vector<int> rc(n, AGPU_OK);
+  std::vector<std::thread> th;
+  for (int r = 1; r < n; r++) th.emplace_back([&, r] { rc[r] = f(r); });
+  rc[0] = f(0);
+  for (auto& t : th) t.join();
+  int out = AGPU_OK;
+  for (int r = 0; r < n; r++)
+    if (rc[r] != AGPU_OK && (out == AGPU_OK || out == AGPU_ERR_ILLEGAL_MOVE)) { out = rc[r]; m->err = m->ctx[r]->eng->err; }
+  return out;
+}
+
+static int multi_run(agpu_multi* m, int32_t slot, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct, uint64_t seed,
+                     agpu_samples* samples, int64_t results[3], agpu_run_stats* stats, bool duel, int32_t slot_b) {
+  if (!m || !results || ngames < 1) return AGPU_ERR_INVALID;
+  const int n = (int)m->ctx.size();
+  std::vector<int64_t> res(3 * (size_t)n, 0);
+  std::vector<agpu_run_stats> st((size_t)n);
+  for (auto& s : st) memset(&s, 0, sizeof(s));
+  // phase 1: every device plays its block of games to the end; the samples stay in its memory
+  const int rc1 = multi_for_each(m, [&](int r) {
+    int64_t base, count;
+    shard_block(ngames, n, r, &base, &count);
+    if (count == 0) return (int)AGPU_OK;
+    return m->ctx[r]->eng->selfplay(slot, visits, count, uid_base + (uint32_t)base, cpuct, seed, nullptr, &res[3 * (size_t)r], &st[(size_t)r], duel, slot_b);
+  });
+  if (rc1 != AGPU_OK && rc1 != AGPU_ERR_ILLEGAL_MOVE) return rc1;
+  results[0] = results[1] = results[2] = 0;
+  agpu_run_stats tot;
+  memset(&tot, 0, sizeof(tot));
+  std::vector<int64_t> offset((size_t)n + 1, 0);
+  for (int r = 0; r < n; r++) {
+    for (int i = 0; i < 3; i++) results[i] += res[3 * (size_t)r + i];
+    tot.sims += st[r].sims; tot.positions += st[r].positions; tot.total_length += st[r].total_length; tot.faults += st[r].faults;
+    tot.kernel_launches += st[r].kernel_launches;
+    tot.plies = std::max(tot.plies, st[r].plies); tot.device_ms = std::max(tot.device_ms, st[r].device_ms);
+    int64_t base, count;
+    shard_block(ngames, n, r, &base, &count);
+    offset[(size_t)r + 1] = offset[(size_t)r] + (count > 0 && !duel ? m->ctx[r]->eng->last_samples() : 0);
+  }
+  if (stats) *stats = tot;
+  // phase 2: the gather — every device copies its block to its place in the caller's arrays (device order = ascending uid blocks)
+  if (samples && !duel) {
+    samples->count = offset[(size_t)n];
+    const int rc2 = multi_for_each(m, [&](int r) { return m->ctx[r]->eng->fetch_samples(samples, offset[(size_t)r]); });
+    if (rc2 != AGPU_OK) return rc2;
+  }
+  return rc1;
 }
 
 extern "C" {
@@ -196,6 +263,55 @@ int agpu_layout_info(agpu_ctx* ctx, int64_t* node_bytes, int64_t* game_bytes, in
   CTX_OR_FAIL();
   return ctx->eng->layout_info(node_bytes, game_bytes, lanes_per_game);
 }
+int agpu_multi_create(agpu_multi** out, const agpu_config* cfg, int32_t ngpus, const int32_t* devices) {
+  if (!out || !cfg || ngpus < 1 || ngpus > 64) { g_create_error = "bad arguments"; return AGPU_ERR_INVALID; }
+  *out = nullptr;
+  agpu_multi* m = new agpu_multi;
+  for (int r = 0; r < ngpus; r++) {
+    agpu_config c = *cfg;
+    c.device = devices ? devices[r] : r;
+    c.max_games = (cfg->max_games + ngpus - 1) / ngpus;                 // the largest shard
+    agpu_ctx* x = nullptr;
+    const int rc = agpu_create(&x, &c);
+    if (rc != AGPU_OK) {
+      for (agpu_ctx* y : m->ctx) agpu_destroy(y);
+      delete m;
+      return rc;                                                        // message in agpu_last_error(NULL)
+    }
+    m->ctx.push_back(x);
+  }
+  *out = m;
+  return AGPU_OK;
+}
+void agpu_multi_destroy(agpu_multi* m) {
+  if (!m) return;
+  for (agpu_ctx* x : m->ctx) agpu_destroy(x);
+  delete m;
+}
+const char* agpu_multi_last_error(const agpu_multi* m) { return m ? m->err.c_str() : g_create_error.c_str(); }
+int agpu_multi_ngpus(const agpu_multi* m) { return m ? (int)m->ctx.size() : 0; }
+agpu_ctx* agpu_multi_context(agpu_multi* m, int32_t index) { return (m && index >= 0 && index < (int)m->ctx.size()) ? m->ctx[index] : nullptr; }
+
+int agpu_multi_set_weights(agpu_multi* m, int32_t slot, const float* base, const float* const* res, const float* pol_w, const float* pol_b,
+                           const float* val_w, const float* val_b) {
+  if (!m) return AGPU_ERR_INVALID;
+  for (agpu_ctx* x : m->ctx) {
+    const int rc = x->eng->set_weights(slot, base, res, pol_w, pol_b, val_w, val_b);
+    if (rc != AGPU_OK) { m->err = x->eng->err; return rc; }
+  }
+  return AGPU_OK;
+}
+
+int agpu_multi_selfplay(agpu_multi* m, int32_t slot, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct, float noise, uint64_t seed,
+                        agpu_samples* samples, int64_t results[3], agpu_run_stats* stats) {
+  (void)noise;
+  return multi_run(m, slot, visits, ngames, uid_base, cpuct, seed, samples, results, stats, false, 0);
+}
+int agpu_multi_duel(agpu_multi* m, int32_t slot_a, int32_t slot_b, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct, uint64_t seed,
+                    int64_t results[3], agpu_run_stats* stats) {
+  return multi_run(m, slot_a, visits, ngames, uid_base, cpuct, seed, nullptr, results, stats, true, slot_b);
+}
+
 /* development hook: device buffer receiving clock64 stamps of the tensor-core chain ([cta][tile][16 layers][4]); NULL disables */
 int agpu_debug_tc_trace(void* dev_buf) { ag::g_tc_dbg = (long long*)dev_buf; return AGPU_OK; }
 /* test hook: the canonical exp / sigmoid evaluated on the device */

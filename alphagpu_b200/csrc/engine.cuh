@@ -60,6 +60,8 @@ struct EngineBase {
   virtual int get_tree(int64_t L, agpu_tree_dump* out) = 0;
   virtual int selfplay(int slot, int visits, int64_t ngames, uint32_t uid_base, float cpuct, uint64_t seed, agpu_samples* samples,
                        int64_t results[3], agpu_run_stats* stats, bool duel, int slot_b) = 0;
+  virtual int fetch_samples(agpu_samples* out, int64_t row_offset) = 0;
+  virtual int64_t last_samples() const = 0;
   virtual int profile(int enable) = 0;
   virtual int kernel_times(agpu_kernel_times* out, int reset) = 0;
   virtual int layout_info(int64_t* node_bytes, int64_t* game_bytes, int64_t* lanes) = 0;
@@ -120,6 +122,7 @@ struct EngineT : EngineBase {
   DevBuf<int32_t> d_i32;
   DevBuf<unsigned long long> tallies, counters;
   DevBuf<uint8_t> path_node, path_move, path_len;
+  int64_t last_sample_count = 0;   // rows the last self-play run left in the device sample arrays (agpu_multi_selfplay gathers them)
   float last_cpuct = 2.0f;   // cpuct of the most recent descent: the backup re-solves π̄ with it (FAST layouts)
   int32_t* total_host = nullptr;   // pinned
   unsigned long long* fault_host = nullptr;   // pinned: tallies[4] of the ply just played ("faute", mcts_gpu.jl:526-529)
@@ -819,6 +822,7 @@ struct EngineT : EngineBase {
       stats->sims = sims; stats->positions = npos; stats->plies = round; stats->total_length = (int64_t)tallies_host[3];
       stats->faults = (int64_t)tallies_host[4]; stats->kernel_launches = launch_count - launches0; stats->device_ms = ms; stats->search_ms = 0.0;
     }
+    last_sample_count = duel ? 0 : std::min<long long>(count, cap);
     if (samples) {
       samples->count = count;
       const long long rows = std::min<long long>(count, std::min<long long>(samples->capacity, cap));
@@ -847,6 +851,28 @@ struct EngineT : EngineBase {
     }
     return AGPU_OK;
   }
+
+  // the rows of the last self-play run, still resident in the device sample arrays, copied to out's arrays starting at row_offset
+  // (agpu_multi_selfplay: every device's block lands at its place in the caller's buffers over that device's own PCIe link)
+  int fetch_samples(agpu_samples* out, int64_t row_offset) override {
+    AG_REQUIRE(out && row_offset >= 0, AGPU_ERR_INVALID, "bad arguments");
+    AG_CK(cudaSetDevice(cfg.device));
+    const long long rows = std::min<long long>(last_sample_count, out->capacity - row_offset);
+    if (rows <= 0) return AGPU_OK;
+    AG_REQUIRE(out->state && out->policy && out->player && out->value && out->fstate, AGPU_ERR_INVALID, "null sample array");
+    const long long o = row_offset;
+    AG_CK(cudaMemcpyAsync(out->state + o * 2 * G::VS, s_state.p, (size_t)rows * 2 * G::VS, cudaMemcpyDeviceToHost, stream));
+    AG_CK(cudaMemcpyAsync(out->policy + o * A, s_policy.p, sizeof(float) * rows * A, cudaMemcpyDeviceToHost, stream));
+    AG_CK(cudaMemcpyAsync(out->player + o, s_player.p, rows, cudaMemcpyDeviceToHost, stream));
+    AG_CK(cudaMemcpyAsync(out->value + o, s_value.p, sizeof(float) * rows, cudaMemcpyDeviceToHost, stream));
+    AG_CK(cudaMemcpyAsync(out->fstate + o * G::FS, s_fstate.p, (size_t)rows * G::FS, cudaMemcpyDeviceToHost, stream));
+    if (out->game) AG_CK(cudaMemcpyAsync(out->game + o, s_game.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream));
+    if (out->ply) AG_CK(cudaMemcpyAsync(out->ply + o, s_ply.p, sizeof(int32_t) * rows, cudaMemcpyDeviceToHost, stream));
+    AG_CK(cudaStreamSynchronize(stream));
+    return AGPU_OK;
+  }
+
+  int64_t last_samples() const override { return last_sample_count; }
 
   int profile(int enable) override {
     AG_CK(cudaSetDevice(cfg.device));

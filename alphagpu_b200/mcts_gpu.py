@@ -224,6 +224,75 @@ class Context:
         return y
 
 
+class MultiContext:
+    """`ngpus` devices behind one call from one process (agpu_multi_*, include/alphagpu.h): one context, host thread and stream per
+    device inside the library; games block-partitioned by uid, samples gathered into the caller's arrays in ascending uid blocks.
+    The reference's caller (selfplay.jl:34) stays one process doing one call per generation."""
+
+    def __init__(self, spec: GameSpec, visits: int, ngames: int, width: int, blocks: int, ngpus: int, devices=None, nn_mode: int = _lib.NN_FP16_TC):
+        self.lib = _lib.load()
+        self.spec, self.visits, self.ngames, self.ngpus = spec, visits, ngames, ngpus
+        self.width, self.blocks = width, blocks
+        self.A, self.VS, self.FS = spec.maxActions, spec.VectorizedState, spec.FeatureSize
+        cfg = _lib.Config(spec.game, spec.N, spec.Nvict, visits, ngames, width, blocks, 0, nn_mode)
+        dev = None if devices is None else (C.c_int32 * ngpus)(*devices)
+        h = C.c_void_p()
+        rc = self.lib.agpu_multi_create(C.byref(h), C.byref(cfg), ngpus, dev)
+        if rc != _lib.OK:
+            msg = self.lib.agpu_multi_last_error(None)
+            raise _lib.AlphaGPUError(rc, msg.decode() if msg else "")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.agpu_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, allow=()):
+        if rc != _lib.OK and rc not in allow:
+            msg = self.lib.agpu_multi_last_error(self.h)
+            raise _lib.AlphaGPUError(rc, msg.decode() if msg else "")
+
+    def set_weights(self, net: SNetwork2, slot: int = 0):
+        n, k, inp = self.width, self.blocks, 2 * self.VS
+        if not (net.base.shape == (n, inp) and len(net.res) == k and net.policy.shape == (self.A, n) and net.value.shape == (1, n)):
+            raise ValueError(f"set_weights: the actor does not match this context ({n}x{k}, {inp} inputs, {self.A} actions)")
+        arr = (C.c_void_p * max(1, net.blocks))(*[r.ctypes.data for r in net.res])
+        self._check(self.lib.agpu_multi_set_weights(self.h, slot, _p(net.base), C.cast(arr, C.c_void_p), _p(net.policy), _p(net.policy_bias),
+                                                    _p(net.value), _p(net.value_bias)))
+
+    def selfplay(self, visits: int, ngames: int, *, cpuct=2.0, noise=0.0, seed=0, uid_base=0, slot=0, want_samples=True, out=None):
+        res = np.zeros(3, np.int64)
+        st = _lib.RunStats()
+        if want_samples or out is not None:
+            if out is None:
+                cap = ngames * self.spec.maxLengthGame
+                out = dict(state=np.empty((cap, 2 * self.VS), np.int8), policy=np.empty((cap, self.A), np.float32), player=np.empty(cap, np.int8),
+                           value=np.empty(cap, np.float32), fstate=np.empty((cap, self.FS), np.int8), game=np.empty(cap, np.int32), ply=np.empty(cap, np.int32))
+            cap = out["player"].shape[0]
+            sc = _lib.Samples(cap, 0, *[out[k].ctypes.data for k in ("state", "policy", "player", "value", "fstate", "game", "ply")])
+            rc = self.lib.agpu_multi_selfplay(self.h, slot, visits, ngames, uid_base, cpuct, noise, seed, C.byref(sc), _p(res), C.byref(st))
+            n = min(int(sc.count), cap)
+            out = {k: v[:n] for k, v in out.items()}
+        else:
+            rc = self.lib.agpu_multi_selfplay(self.h, slot, visits, ngames, uid_base, cpuct, noise, seed, None, _p(res), C.byref(st))
+        self._check(rc, allow=(_lib.ERR_ILLEGAL_MOVE,))
+        return res, {k: getattr(st, k) for k, _ in _lib.RunStats._fields_}, out
+
+    def duel(self, visits: int, ngames: int, *, slot_a=0, slot_b=1, cpuct=2.0, seed=0, uid_base=0):
+        res = np.zeros(3, np.int64)
+        st = _lib.RunStats()
+        rc = self.lib.agpu_multi_duel(self.h, slot_a, slot_b, visits, ngames, uid_base, cpuct, seed, _p(res), C.byref(st))
+        self._check(rc, allow=(_lib.ERR_ILLEGAL_MOVE,))
+        return res, {k: getattr(st, k) for k, _ in _lib.RunStats._fields_}
+
+
 # ------------------------------------------------------------------------------------------------
 # The reference's public entry points
 # ------------------------------------------------------------------------------------------------
@@ -280,14 +349,31 @@ def _empty_run(spec: GameSpec):
 
 
 def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample], *, spec: GameSpec, cpuct=2.0, noise=None, seed=None,
-         uid_base=0, device=0, nn_mode=_lib.NN_FP16_TC, ctx: Optional[Context] = None):
+         uid_base=0, device=0, nn_mode=_lib.NN_FP16_TC, ctx=None, ngpus: int = 1):
     """mcts(actor, visits, ngames, buffer; cpuct, noise) (mcts_gpu.jl:477-579): one generation of self-play; samples are
     pushed into `buffer`.  Returns (data, valid) like the reference plus the run statistics.
 
     Under torch.distributed (one process per GPU) the `ngames` games are block-partitioned over the ranks by uid — no collective on
     the search path — and the sample blocks are all-gathered afterwards, so every rank pushes the same samples in the same order
-    (rank-major) into its buffer; results and counters are summed over ranks."""
+    (rank-major) into its buffer; results and counters are summed over ranks.
+
+    `ngpus` > 1 (outside torch.distributed): one process drives that many devices through agpu_multi_selfplay — the library runs one
+    host thread per device and gathers the samples itself (`ctx` may be a MultiContext to reuse)."""
     rank, world, backend = _world()
+    if world == 1 and (ngpus > 1 or isinstance(ctx, MultiContext)):
+        seed = _fresh_seed(seed, device, backend)
+        own = ctx is None
+        if own:
+            ctx = MultiContext(spec, visits, ngames, actor.width, actor.blocks, ngpus, nn_mode=nn_mode)
+        ctx.set_weights(actor, 0)
+        noise = float(2.0 / spec.maxActions) if noise is None else noise
+        res, stats, out = ctx.selfplay(visits, ngames, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
+        if buffer is not None:
+            buffer.push_block(out["state"], out["policy"], out["player"], out["value"], out["fstate"])
+        if own:
+            ctx.close()
+        stats["results"] = res
+        return dict(data=[], valid=stats["faults"] == 0, stats=stats)
     if world > 1:
         from .parallel import gather_samples, shard_games
         base, count = shard_games(ngames, rank, world)

@@ -190,6 +190,27 @@ int agpu_selfplay(agpu_ctx* ctx, int32_t slot, int32_t visits, int64_t ngames, u
 int agpu_duel(agpu_ctx* ctx, int32_t slot_a, int32_t slot_b, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct,
               uint64_t seed, int64_t results[3], agpu_run_stats* stats);
 
+/* ---- several GPUs behind one call ------------------------------------------------------------
+ * The reference is one process on one GPU (selfplay.jl:34 calls mcts_gpu.mcts once per generation).  The same single call can drive
+ * `ngpus` devices: one context per device inside the library, one host thread and one stream per device, the `ngames` games
+ * block-partitioned over the devices by uid (results do not depend on the partition: the RNG is keyed by uid), no collective on the
+ * search path, and the sample gather done here — every device copies its block to its place in the caller's arrays (device order =
+ * ascending uid blocks; within a block, push order).  cfg->max_games is the TOTAL number of games; cfg->device is ignored
+ * (devices[r], or r when devices is NULL). */
+typedef struct agpu_multi agpu_multi;
+int agpu_multi_create(agpu_multi** out, const agpu_config* cfg, int32_t ngpus, const int32_t* devices);
+void agpu_multi_destroy(agpu_multi* m);
+const char* agpu_multi_last_error(const agpu_multi* m);
+int agpu_multi_ngpus(const agpu_multi* m);
+agpu_ctx* agpu_multi_context(agpu_multi* m, int32_t index);   /* the per-device context, e.g. for agpu_get_kernel_times */
+int agpu_multi_set_weights(agpu_multi* m, int32_t slot, const float* base, const float* const* res, const float* pol_w, const float* pol_b,
+                           const float* val_w, const float* val_b);
+/* == agpu_selfplay / agpu_duel over all devices; stats: sums, except plies and device_ms = max over devices */
+int agpu_multi_selfplay(agpu_multi* m, int32_t slot, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct, float noise,
+                        uint64_t seed, agpu_samples* samples, int64_t results[3], agpu_run_stats* stats);
+int agpu_multi_duel(agpu_multi* m, int32_t slot_a, int32_t slot_b, int32_t visits, int64_t ngames, uint32_t uid_base, float cpuct,
+                    uint64_t seed, int64_t results[3], agpu_run_stats* stats);
+
 /* ---- measurement --------------------------------------------------------------------------- */
 #define AGPU_NKERNELS 8
 typedef struct agpu_kernel_times {

@@ -95,21 +95,66 @@ end
 
 # mcts(actor, visits, ngames, buffer; cpuct, noise) (mcts_gpu.jl:477-579): one generation of self-play, whole ply loop on the GPU;
 # samples are pushed into `buffer` with push_buffer/update_buffer semantics (main4IARow.jl:49-75)
-function mcts(actor, visits, ngames, buffer::Main.PoolSample; θ=1, cpuct=2.0, noise=Float32(1 / maxActions), seed=rand(UInt64))
-    ctx = init(ngames, visits, actor)
+# Contexts are kept between calls — one per (ngames, visits, width, blocks, ngpus) — so that a generation does not pay for the allocation
+# of the tree arrays again (the reference allocates per call, mcts_gpu.jl:481; its arrays are 1.6 GiB at 32768 games); only the weights
+# are uploaded each time.  NGPUS[] > 1 drives that many devices from this one process through agpu_multi_* (the library runs one host
+# thread per device and gathers the samples itself).
+const NGPUS = Ref(1)
+const CONTEXTS = Dict{NTuple{5,Int},Context}()
+const MULTI = Dict{NTuple{5,Int},Ptr{Cvoid}}()
+function cached_context(ngames, visits, actor)
+    key = (Int(ngames), Int(visits), size(actor.base, 1), length(actor.res), 1)
+    ctx = get!(CONTEXTS, key) do
+        init(ngames, visits, actor)
+    end
+    set_weights!(ctx, actor, 0)
+    return ctx
+end
+function cached_multi(ngames, visits, actor, ngpus)
+    key = (Int(ngames), Int(visits), size(actor.base, 1), length(actor.res), Int(ngpus))
+    h = get!(MULTI, key) do
+        cfg = Ref(AgpuConfig(GAME_ID, GAME_N, GAME_NVICT, visits, ngames, size(actor.base, 1), length(actor.res), 0, 2))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = ccall((:agpu_multi_create, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ptr{AgpuConfig}, Int32, Ptr{Int32}), out, cfg, ngpus, C_NULL)
+        rc == 0 || error("agpu_multi_create: ", unsafe_string(ccall((:agpu_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        out[]
+    end
+    return h
+end
+function multi_set_weights!(h, actor, slot)
+    base, res = actor.base, actor.res
+    pol, polb, val, valb = actor.policy, actor.policy_bias, actor.value, actor.value_bias
+    resptr = [pointer(w) for w in res]
+    GC.@preserve base res pol polb val valb resptr begin
+        rc = ccall((:agpu_multi_set_weights, LIB), Cint,
+                   (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Ptr{Float32}}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}),
+                   h, slot, base, resptr, pol, polb, val, valb)
+        rc == 0 || error("agpu_multi_set_weights: ", unsafe_string(ccall((:agpu_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), h)))
+    end
+end
+
+function mcts(actor, visits, ngames, buffer::Main.PoolSample; θ=1, cpuct=2.0, noise=Float32(1 / maxActions), seed=rand(UInt64), ngpus=NGPUS[])
+    multi = ngpus > 1
+    ctx = multi ? nothing : cached_context(ngames, visits, actor)
+    mh = multi ? cached_multi(ngames, visits, actor, ngpus) : C_NULL
+    multi && multi_set_weights!(mh, actor, 0)
     cap = ngames * maxLengthGame
     state = Array{Int8}(undef, 2 * VectorizedState, cap); policy = Array{Float32}(undef, maxActions, cap)
     player = Array{Int8}(undef, cap); value = Array{Float32}(undef, cap); fstate = Array{Int8}(undef, FeatureSize, cap)
     smp = AgpuSamples(cap, 0, pointer(state), pointer(policy), pointer(player), pointer(value), pointer(fstate), C_NULL, C_NULL)
     results = zeros(Int64, 3); stats = AgpuRunStats()
-    rc = GC.@preserve state policy player value fstate ccall((:agpu_selfplay, LIB), Cint,
-        (Ptr{Cvoid}, Int32, Int32, Int64, UInt32, Float32, Float32, UInt64, Ref{AgpuSamples}, Ptr{Int64}, Ref{AgpuRunStats}),
-        ctx.h, 0, visits, ngames, 0, Float32(cpuct), Float32(noise), seed, smp, results, stats)
+    rc = GC.@preserve state policy player value fstate (multi ?
+        ccall((:agpu_multi_selfplay, LIB), Cint,
+              (Ptr{Cvoid}, Int32, Int32, Int64, UInt32, Float32, Float32, UInt64, Ref{AgpuSamples}, Ptr{Int64}, Ref{AgpuRunStats}),
+              mh, 0, visits, ngames, 0, Float32(cpuct), Float32(noise), seed, smp, results, stats) :
+        ccall((:agpu_selfplay, LIB), Cint,
+              (Ptr{Cvoid}, Int32, Int32, Int64, UInt32, Float32, Float32, UInt64, Ref{AgpuSamples}, Ptr{Int64}, Ref{AgpuRunStats}),
+              ctx.h, 0, visits, ngames, 0, Float32(cpuct), Float32(noise), seed, smp, results, stats))
     if rc == -5      # AGPU_ERR_ILLEGAL_MOVE == the reference's "faute" (mcts_gpu.jl:526-529)
         println("faute")
         return (data=[], valid=false)
     end
-    check(ctx.h, rc)
+    multi ? (rc == 0 || error(unsafe_string(ccall((:agpu_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), mh)))) : check(ctx.h, rc)
     for s in 1:smp.count          # push_buffer + update_buffer, ring semantics of main4IARow.jl:49-75
         index = buffer.currentIndex
         buffer.pool[index].state .= @view state[:, s]
@@ -128,7 +173,7 @@ end
 
 # mcts(actor1, actor2, visits, ngames; cpuct, noise, conv) (mcts_gpu.jl:581-651) -> [v, n, d]
 function mcts(actor1, actor2, visits, ngames; cpuct=2f0, noise=Float32(1 / maxActions), conv=2, seed=rand(UInt64))
-    ctx = init(ngames, visits, actor1)
+    ctx = cached_context(ngames, visits, actor1)
     set_weights!(ctx, actor2, 1)
     results = zeros(Int64, 3); stats = AgpuRunStats()
     rc = ccall((:agpu_duel, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Int32, Int64, UInt32, Float32, UInt64, Ptr{Int64}, Ref{AgpuRunStats}),
