@@ -9,6 +9,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges show up in nsys / ncu --nvtx timelines, no-ops without a tool attached
+
 #include "../../include/alphagpu.h"
 #include "nn.cuh"
 #include "search.cuh"
@@ -28,6 +30,12 @@ enum { K_SELECT = 0, K_NN = 1, K_EXPAND = 2, K_BEGIN = 3, K_FINISH = 4, K_COMPAC
       return AGPU_ERR_CUDA;                                                                              \
     }                                                                                                    \
   } while (0)
+
+// NVTX range for the enclosing scope (the reference brackets its phases with time() stamps, mcts_gpu.jl:377-445)
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 #define AG_REQUIRE(cond, code, msg) \
   do {                              \
@@ -585,6 +593,7 @@ struct EngineT : EngineBase {
     const float* dprob;
     int rc = upload_prob(prob, L, visits, &dprob);
     if (rc != AGPU_OK) return rc;
+    NvtxRange nv_search("agpu_search (mcts_single)");
     launch(K_BEGIN, [&] { root_reset_kernel<G><<<blocks_for_threads(L), 256, 0, stream>>>(P, (int)L, nullptr, nullptr); });
     rc = (use_fused && !dprob) ? enqueue_search_fused(L, slot, visits, training, cpuct, seed, ply)
          : (dprob || profiling || nseg <= 1) ? enqueue_search(L, slot, visits, training, cpuct, dprob, seed, ply)
@@ -771,7 +780,11 @@ struct EngineT : EngineBase {
     if (trace_plies) t_prev = now_ms();
     const bool streaming = stream_samples && !duel && samples != nullptr && samples->capacity > 0;
     if (streaming) AG_REQUIRE(samples->state && samples->policy && samples->player && samples->value && samples->fstate, AGPU_ERR_INVALID, "null sample array");
+    NvtxRange nv_loop(duel ? "agpu_duel" : "agpu_selfplay");
     while (L > 0) {
+      char nv_name[48];
+      snprintf(nv_name, sizeof(nv_name), "ply %u (%lld games)", round, (long long)L);
+      NvtxRange nv_ply(nv_name);
       const int actor = duel ? ((round % 2 == 0) ? slot : slot_b) : slot;                  // :592-596
       int rc = use_fused ? enqueue_search_fused(L, actor, visits, duel ? 0 : 1, cpuct, seed, round)                     // mcts_single (:503, :599)
                : (profiling || nseg <= 1) ? enqueue_search(L, actor, visits, duel ? 0 : 1, cpuct, nullptr, seed, round)
@@ -779,6 +792,7 @@ struct EngineT : EngineBase {
       if (rc != AGPU_OK) return rc;
       sims += L * visits; npos += L;
       const int nb = blocks_for_threads(L);
+      nvtxRangePushA("move + compaction");
       if (duel) launch(K_FINISH, [&] { finish_ply_kernel<G, true><<<nb, 256, 0, stream>>>(P, (int)L, round, seed, uid_base, S, count, Y); });
       else launch(K_FINISH, [&] { finish_ply_kernel<G, false><<<nb, 256, 0, stream>>>(P, (int)L, round, seed, uid_base, S, count, Y); });
       launch(K_COMPACT, [&] { scan_blocks_kernel<<<1, 1024, 0, stream>>>(block_count.p, nb, total_dev.p); });
@@ -786,6 +800,7 @@ struct EngineT : EngineBase {
       AG_CK(cudaMemcpyAsync(total_host, total_dev.p, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
       AG_CK(cudaMemcpyAsync(fault_host, tallies.p + 4, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
       AG_CK(cudaStreamSynchronize(stream));                                                  // one host sync per ply (the reference: 6·R+3)
+      nvtxRangePop();
       if (streaming) {                                                                       // this ply's rows [count, count + L) are final
         const long long lo = count, hi = std::min<long long>(count + L, std::min<long long>(samples->capacity, cap));
         if (hi > lo) {
