@@ -38,6 +38,12 @@ AG_HD u64 hdr_word(int parent, int action, int nchild, int flags, int result) {
   return (u64)(uint8_t)parent | ((u64)(uint8_t)action << 8) | ((u64)(uint8_t)nchild << 16) | ((u64)(uint8_t)flags << 24) | ((u64)(uint8_t)(int8_t)result << 32);
 }
 AG_D void hdr_store(void* p, u64 w) { *reinterpret_cast<u64*>(p) = w; }
+struct alignas(8) NodeAux {
+  float rem;         // Σ_{a: no child} prior[a], ascending action order
+  uint16_t acount;   // #{a: prior[a] > 0}
+  uint16_t nvis;     // Σ_a visits[a]
+};
+static_assert(sizeof(NodeAux) == 8, "aux");
 AG_D NodeHdr hdr_from_word(u64 w) { NodeHdr h; *reinterpret_cast<u64*>(&h) = w; return h; }
 
 constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
@@ -87,8 +93,12 @@ struct Layout {
   static constexpr int OFF_HDR = FAST ? OFF_HDR_F : OFF_STATE + (int)sizeof(typename G::State);
   static constexpr int STATS_BEGIN = FAST ? 8 : 0;                     // [STATS_BEGIN, STATS_END): zeroed when a root is installed
   static constexpr int STATS_END = OFF_STATE;
+  // Large action sets: 8 more bytes behind the header cache what the α-solve would otherwise recompute from A-long arrays at every
+  // visited level — prior_rem = Σ prior over the actions without a child (ascending action order, mcts_gpu.jl:122-124; it changes only
+  // when a child is created), #{prior > 0} (:128-130; fixed by expand) and Σ visits (:118-120; +1 per backup through the node).
+  static constexpr int OFF_AUX = OFF_HDR + 8;
   static constexpr int REC = FAST ? (OFF_STATE + (int)sizeof(typename G::State) + 63) / 64 * 64
-                                  : (OFF_HDR + 8 + 31) / 32 * 32;     // record size
+                                  : (OFF_AUX + 8 + 31) / 32 * 32;     // record size
   static constexpr int OUTS = (A + 1 + 3) / 4 * 4;                 // floats per game of network output: logits[A], value
   static_assert(sizeof(typename G::State) % 8 == 0, "state alignment");
 };
@@ -224,6 +234,7 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
   // zero the statistics (prior, q, visits, child, order, π̄)
   for (int o = Lay::STATS_BEGIN; o < Lay::STATS_END; o += 8) *reinterpret_cast<uint2*>(rec + o) = make_uint2(0, 0);
   hdr_store(rec + Lay::OFF_HDR, 0ull);
+  if (!Lay::FAST) hdr_store(rec + Lay::OFF_AUX, 0ull);
   P.nnodes[g] = 1;
   P.leaf[g] = 0;
 }
@@ -381,37 +392,22 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
       // the next node is one of the children: pull their first sectors towards L1 while this level is sampled
       if (ch[0] != 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(gbase + (size_t)(ch[0] - 1) * REC));
     } else {
+    // what the solve needs from A-long sums is cached behind the header (NodeAux): Σ visits, prior_rem, #{prior > 0}
+    const NodeAux ax = *reinterpret_cast<const NodeAux*>(rec + Lay::OFF_AUX);
 #pragma unroll
     for (int j = 0; j < APL; j++) {
       const int a = j * W + l;
       const bool in = a < A;
       p[j] = in ? *reinterpret_cast<const float*>(rec + Lay::OFF_PRIOR + 4 * a) : 0.f;
       q[j] = in ? *reinterpret_cast<const float*>(rec + Lay::OFF_Q + 4 * a) : 0.f;
-      vis[j] = in ? (int)*reinterpret_cast<const uint16_t*>(rec + Lay::OFF_VIS + 2 * a) : 0;
       ch[j] = in ? (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_CHILD + a) : 0;
       ord[j] = in ? (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_ORDER + a) : 0;
     }
-    int nv = 0;
-#pragma unroll
-    for (int j = 0; j < APL; j++) nv += vis[j];
-    nv = gsum<W>(gm, nv);
-
-    if (nv > 0) {                                                          // uptodate != 1  (:114): some backup passed through
+    if (ax.nvis > 0) {                                                     // uptodate != 1  (:114): some backup passed through
       // n = 1 + Σ visits (exact), prior_rem = Σ_{no child} prior in ascending action order, A = #{prior > 0}   (:116-131)
-      const float n = (float)(1 + nv);
-      float rem = 0.f;
-      int acount = 0;
-#pragma unroll
-      for (int j = 0; j < APL; j++) {
-        const float contrib = (ch[j] == 0) ? p[j] : 0.f;
-        acount += gcount<W>(gm, p[j] > 0.f);
-#pragma unroll
-        for (int s = 0; s < W; s++) {
-          if (j * W + s < A) rem = fadd(rem, gshfl<W>(gm, contrib, s));
-        }
-      }
-      const float lambda = fdiv(fmul(cpuct, fsqrt(n)), fadd((float)acount, n));   // :132
-      rem = fmul(rem, lambda);                                                       // :134
+      const float n = (float)(1 + (int)ax.nvis);
+      const float lambda = fdiv(fmul(cpuct, fsqrt(n)), fadd((float)ax.acount, n));   // :132
+      const float rem = fmul(ax.rem, lambda);                                        // :134
       float alpha = 0.f;                                                             // :135-138
       float top[APL];
 #pragma unroll
@@ -420,22 +416,41 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
         if (j * W + l < A) alpha = fmaxf(alpha, fadd(q[j], fmaxf(top[j], 1e-4f)));
       }
       alpha = gmax<W>(gm, alpha);
-      float err = __int_as_float(0x7f800000);
+      // The Newton sums run over the CHILDREN only, in creation (slot) order: lane l gathers the statistics of the children in slots
+      // l, l + W, … once, so that an iteration costs two divisions per lane and slot group instead of two per lane and action group.
       const int nchild = h.nchild;
+      const int ngroups = (nchild + W - 1) / W;                                      // warp-uniform, <= APL
+      float ctop[APL], cq[APL];
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        ctop[j] = 0.f; cq[j] = 0.f;
+        if (j < ngroups) {
+          const int a = (j * W + l < nchild) ? ord[j] - 1 : 0;
+          const int srcl = a % W, srci = a / W;
+#pragma unroll
+          for (int jj = 0; jj < APL; jj++) {
+            const float vq = gshfl<W>(gm, q[jj], srcl), vt = gshfl<W>(gm, top[jj], srcl);
+            if (srci == jj) { cq[j] = vq; ctop[j] = vt; }
+          }
+        }
+      }
+      float err = __int_as_float(0x7f800000);
       for (int it = 0; it < 100; it++) {                                             // :141-162
         float S = fdiv(rem, alpha);
         float gs = fdiv(-rem, fmul(alpha, alpha));
         float t1[APL], t2[APL];
 #pragma unroll
         for (int j = 0; j < APL; j++) {
-          const float bot = fsub(alpha, q[j]);
-          t1[j] = fdiv(top[j], bot);
-          t2[j] = fdiv(-top[j], fmul(bot, bot));
+          t1[j] = 0.f; t2[j] = 0.f;
+          if (j < ngroups) {
+            const float bot = fsub(alpha, cq[j]);
+            t1[j] = fdiv(ctop[j], bot);
+            t2[j] = fdiv(-ctop[j], fmul(bot, bot));
+          }
         }
         for (int k = 0; k < nchild; k++) {                                           // children in creation (slot) order
-          const int a = gshfl<W>(gm, pick<APL>(ord, k / W), k % W) - 1;
-          S = fadd(S, gshfl<W>(gm, pick<APL>(t1, a / W), a % W));
-          gs = fadd(gs, gshfl<W>(gm, pick<APL>(t2, a / W), a % W));
+          S = fadd(S, gshfl<W>(gm, pick<APL>(t1, k / W), k % W));
+          gs = fadd(gs, gshfl<W>(gm, pick<APL>(t2, k / W), k % W));
         }
         const float newerr = fsub(S, 1.f);
         if (newerr < 0.001f || newerr == err) break;
@@ -466,17 +481,22 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
     // inverse-CDF scan in ascending action order (:172-182)
     float cum = 0.f;
     int best = -1;
-    bool done = false;
+    bool done = false;                                                                // the same on every lane of the group
 #pragma unroll
     for (int j = 0; j < APL; j++) {
 #pragma unroll
-      for (int s = 0; s < W; s++) {
-        if (j * W + s < A) {
-          const float d = gshfl<W>(gm, pol[j], s);
-          if (!done) {
-            cum = fadd(cum, d);
-            if (d > 0.f) best = j * W + s;
-            if (cum >= u) done = true;
+      for (int s8 = 0; s8 < W; s8 += 8) {
+        if (!done) {                                                                  // the rest of the scan changes nothing once the sample is found
+#pragma unroll
+          for (int s = s8; s < s8 + 8 && s < W; s++) {
+            if (j * W + s < A) {
+              const float d = gshfl<W>(gm, pol[j], s);
+              if (!done) {
+                cum = fadd(cum, d);
+                if (d > 0.f) best = j * W + s;
+                if (cum >= u) done = true;
+              }
+            }
           }
         }
       }
@@ -502,6 +522,21 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
         *reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * a) = 0.f;
         *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * a) = 0;
         *reinterpret_cast<uint8_t*>(nrec + Lay::OFF_CHILD + a) = 0;
+      }
+      if constexpr (!Lay::FAST) {
+        // prior_rem of the parent now excludes the new child: the same ascending sum over the actions that still have none
+        float rem = 0.f;
+#pragma unroll
+        for (int j = 0; j < APL; j++) {
+          const float contrib = (ch[j] == 0 && j * W + l != best) ? p[j] : 0.f;
+#pragma unroll
+          for (int s = 0; s < W; s++)
+            if (j * W + s < A) rem = fadd(rem, gshfl<W>(gm, contrib, s));
+        }
+        if (l == 0) {
+          reinterpret_cast<NodeAux*>(rec + Lay::OFF_AUX)->rem = rem;
+          hdr_store(nrec + Lay::OFF_AUX, 0ull);
+        }
       }
       if (l == 0) {
         *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + h.nchild) = (uint8_t)(best + 1);
@@ -597,16 +632,34 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
     }
     const bool rootmix = (leaf == 0) && training;                                       // :259-275
     const float unif = fdiv(0.25f, (float)acount);
+    float prv[APL];
 #pragma unroll
     for (int j = 0; j < APL; j++) {
       const int a = j * W + l;
       float pr = 0.f;
       if (legal[j]) pr = rootmix ? fadd(fdiv(fmul(0.75f, pin[j]), normalize), unif) : fdiv(pin[j], normalize);
+      prv[j] = pr;
       *reinterpret_cast<float*>(rec + Lay::OFF_PRIOR + 4 * a) = pr;
       if (Lay::FAST) *reinterpret_cast<float*>(rec + Lay::OFF_POLICY + 4 * a) = pr;      // policy[:,leaf] = prior[:,leaf]  (:297-299)
       if (leaf == 0 && last_rollout && a < A) P.policy_final[(size_t)g * A + a] = pr;    // R == 1: policy[:,1] is the prior itself
     }
     if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
+    if constexpr (!Lay::FAST) {
+      // NodeAux of the freshly expanded node: no child yet, so prior_rem is the ascending sum of the whole prior; #{prior > 0}; no visits
+      float rem = 0.f;
+      int pos = 0;
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        pos += gcount<W>(gm, prv[j] > 0.f);
+#pragma unroll
+        for (int s = 0; s < W; s++)
+          if (j * W + s < A) rem = fadd(rem, gshfl<W>(gm, prv[j], s));
+      }
+      if (l == 0) {
+        NodeAux ax; ax.rem = rem; ax.acount = (uint16_t)pos; ax.nvis = 0;
+        *reinterpret_cast<NodeAux*>(rec + Lay::OFF_AUX) = ax;
+      }
+    }
   }
 
   LeafEval E;
@@ -1025,6 +1078,8 @@ AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, co
         const float den = fadd(vf, 1.f);
         *qp = (float)__ddiv_rn(__dadd_rn((double)prod, __dsub_rn(1.0, value)), (double)den);
         *vp = (uint16_t)(*vp + 1);
+        uint16_t* nv = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_AUX + 6);            // NodeAux::nvis
+        *nv = (uint16_t)(*nv + 1);
       }
       const NodeHdr nh = *reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR);
       move = nh.action; nindex = nh.parent;
@@ -1040,6 +1095,8 @@ AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, co
         const float vf = (float)*vp;
         *qp = fdiv(fadd(fmul(vf, *qp), fsub(1.f, value)), fadd(vf, 1.f));               // :319
         *vp = (uint16_t)(*vp + 1);                                                       // :320
+        uint16_t* nv = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_AUX + 6);            // NodeAux::nvis
+        *nv = (uint16_t)(*nv + 1);
       }
       const NodeHdr nh = *reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR);
       move = nh.action; nindex = nh.parent;                                              // :322-323
