@@ -196,3 +196,43 @@ def test_tc512_search_runs_config3_shape():
     assert np.array_equal(res, res2) and all(np.array_equal(smp[k], smp2[k]) for k in smp)
     assert np.all(np.abs(smp["policy"].sum(1) - 1) < 2e-3)
     ctx.close()
+
+
+# ---- the north-star bar itself: policies and values within 1e-3 of the fp32 formula (BASELINE.json north_star; DenseNet.jl:294-304) ----
+# Asserted where the tensor-core chain meets it; where it does not, the case is an xfail(strict): the miss is a measured, documented
+# property of the operand format and a silent change in either direction fails the suite.
+_MISS = lambda why: pytest.mark.xfail(strict=True, reason=why)
+NORTH_STAR_CASES = [
+    # width 128: fp32 residual stream, 16-bit MMA operands
+    pytest.param("connect4", 128, 6, 1000, 2, marks=_MISS("fp16 operands, 6 blocks: worst policy entry 1.26e-3 (p99.9 < 1e-3)")),
+    pytest.param("ttt", 128, 6, 300, 2),
+    pytest.param("hex7", 128, 4, 515, 2),
+    pytest.param("reversi8", 128, 2, 256, 2),
+    pytest.param("connect4", 128, 0, 77, 2),
+    pytest.param("connect4", 128, 0, 77, 0),
+    pytest.param("connect4", 128, 6, 1000, 0, marks=_MISS("bf16 operands (8 significand bits): worst entry 1e-2")),
+    pytest.param("ttt", 128, 6, 300, 0, marks=_MISS("bf16 operands: worst entry 8e-3")),
+    pytest.param("hex7", 128, 4, 515, 0, marks=_MISS("bf16 operands: worst entry 6e-3")),
+    # width 512: the residual stream itself is 16-bit (all 512 TMEM columns are accumulators)
+    pytest.param("gobang9", 512, 8, 200, 2),
+    pytest.param("hex7", 512, 0, 130, 2),
+    pytest.param("gobang9", 512, 1, 64, 2),
+    pytest.param("hex7", 512, 8, 300, 2, marks=_MISS("fp16 16-bit residual stream, 8 blocks: worst policy entry 2.7e-3, p99.9 1.9e-3")),
+    pytest.param("reversi8", 512, 8, 260, 2, marks=_MISS("fp16 16-bit residual stream, 8 blocks: worst policy entry 2.4e-3, p99.9 1.4e-3")),
+    pytest.param("hex7", 512, 8, 300, 0, marks=_MISS("bf16 16-bit residual stream: worst entry 2e-2")),
+]
+
+
+@pytest.mark.parametrize("name,n,k,L,nn_mode", NORTH_STAR_CASES)
+def test_tc_chain_meets_the_1e3_tolerance(name, n, k, L, nn_mode):
+    ospec = oracle.Spec(*GAME_SPECS[name])
+    pnet, onet = make_nets(GAME_SPECS[name], n, k, seed=3)
+    ctx = ctx_for(name, 4, 8, n, k, nn_mode)
+    ctx.set_weights(pnet)
+    x = ospec.encode(random_positions(ospec, L, seed=9))
+    logits, v = ctx.forward(x)
+    ctx.close()
+    fl, fv = onet.forward(x, mode=oracle.Net.FP32)
+    dp, dv = np.abs(oracle.softmax(logits) - oracle.softmax(fl)), np.abs(v - fv)
+    print(f"\n{name} {n}x{k} mode {nn_mode}: |Δpolicy| max {dp.max():.2e} p99.9 {np.quantile(dp, 0.999):.2e}; |Δvalue| max {dv.max():.2e}")
+    assert dp.max() <= 1e-3 and dv.max() <= 1e-3
