@@ -434,31 +434,62 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
           }
         }
       }
+      // Divisions: the branch-free fast path (common.cuh: fdiv_fast — correctly rounded inside its operand box, checked against
+      // __fdiv_rn on 2^34 pairs) whenever every operand of every lane is in the box, else the IEEE division; same quotients either way.
+      // The derivative is accumulated with all signs flipped (G = -gs: rounding is sign-symmetric), so every numerator is >= 0.
+      bool num_ok = fdiv_box_num(rem);
+#pragma unroll
+      for (int j = 0; j < APL; j++) num_ok = num_ok && fdiv_box_num(ctop[j]) && fdiv_box_num(top[j]);
+      num_ok = __all_sync(gm, num_ok);
       float err = __int_as_float(0x7f800000);
       for (int it = 0; it < 100; it++) {                                             // :141-162
-        float S = fdiv(rem, alpha);
-        float gs = fdiv(-rem, fmul(alpha, alpha));
-        float t1[APL], t2[APL];
+        const float a2 = fmul(alpha, alpha);
+        float bot[APL], bot2[APL];
+        bool ok = num_ok && fdiv_box_den(alpha) && fdiv_box_den(a2);
 #pragma unroll
         for (int j = 0; j < APL; j++) {
-          t1[j] = 0.f; t2[j] = 0.f;
-          if (j < ngroups) {
-            const float bot = fsub(alpha, cq[j]);
-            t1[j] = fdiv(ctop[j], bot);
-            t2[j] = fdiv(-ctop[j], fmul(bot, bot));
+          bot[j] = fsub(alpha, cq[j]); bot2[j] = fmul(bot[j], bot[j]);
+          if (j < ngroups) ok = ok && fdiv_box_den(bot[j]) && fdiv_box_den(bot2[j]);
+        }
+        ok = __all_sync(gm, ok);
+        float S, G;
+        float t1[APL], t2[APL];
+        if (ok) {
+          S = fdiv_fast(rem, alpha);
+          G = fdiv_fast(rem, a2);
+#pragma unroll
+          for (int j = 0; j < APL; j++) {
+            t1[j] = 0.f; t2[j] = 0.f;
+            if (j < ngroups) { t1[j] = fdiv_fast(ctop[j], bot[j]); t2[j] = fdiv_fast(ctop[j], bot2[j]); }
+          }
+        } else {
+          S = fdiv(rem, alpha);
+          G = fdiv(rem, a2);
+#pragma unroll
+          for (int j = 0; j < APL; j++) {
+            t1[j] = 0.f; t2[j] = 0.f;
+            if (j < ngroups) { t1[j] = fdiv(ctop[j], bot[j]); t2[j] = fdiv(ctop[j], bot2[j]); }
           }
         }
         for (int k = 0; k < nchild; k++) {                                           // children in creation (slot) order
           S = fadd(S, gshfl<W>(gm, pick<APL>(t1, k / W), k % W));
-          gs = fadd(gs, gshfl<W>(gm, pick<APL>(t2, k / W), k % W));
+          G = fadd(G, gshfl<W>(gm, pick<APL>(t2, k / W), k % W));
         }
         const float newerr = fsub(S, 1.f);
         if (newerr < 0.001f || newerr == err) break;
-        alpha = fsub(alpha, fdiv(newerr, gs));
+        // α - err/gs with gs = -G
+        alpha = fadd(alpha, (fdiv_box_num(newerr) && fdiv_box_den(G)) ? fdiv_fast(newerr, G) : fdiv(newerr, G));
         err = newerr;
       }
+      {
+        float den[APL];
+        bool ok = num_ok;
 #pragma unroll
-      for (int j = 0; j < APL; j++) pol[j] = fdiv(top[j], fsub(alpha, q[j]));      // :165-169
+        for (int j = 0; j < APL; j++) { den[j] = fsub(alpha, q[j]); ok = ok && fdiv_box_den(den[j]); }
+        ok = __all_sync(gm, ok);
+#pragma unroll
+        for (int j = 0; j < APL; j++) pol[j] = ok ? fdiv_fast(top[j], den[j]) : fdiv(top[j], den[j]);      // :165-169
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < APL; j++) pol[j] = p[j];                                  // policy == prior until the first backup (:297-299)
