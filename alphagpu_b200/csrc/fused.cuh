@@ -26,7 +26,9 @@ namespace fused {
 using namespace tc;
 
 // -DAG_TRACE=1 builds the development library whose per-ply kernel records clock64 phase traces into the buffer set by
-// agpu_debug_tc_trace (scripts/fused_trace.py); the product library contains none of that code.
+// agpu_debug_tc_trace (scripts/fused_trace.py): per-warp busy time in the search pool and in the descent, phase totals of thread 0.
+// -DAG_TRACE=2 adds the fine-grained stamps of thread 0 inside the descent, the backup items and the layers (they slow its warp down).
+// The product library contains none of that code.
 #ifndef AG_TRACE
 #define AG_TRACE 0
 #endif
@@ -131,6 +133,14 @@ AG_D void epilogue_ordinary(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs
     }
   }
   tmem_st_wait();
+}
+
+// development trace: BAR.SYNC.DEFER_BLOCKING does not block at issue but at the next consumer, so a clock read placed right behind a
+// barrier is early; a volatile shared-memory load in between makes the stamp mean "after the barrier"
+AG_D long long clock_after_barrier(const void* smem_word) {
+  uint32_t d;
+  asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(d) : "r"(smem_u32(smem_word)) : "memory");
+  return clock64() + (long long)(d & 0u);
 }
 
 template <class G, int FMT, int NT>
@@ -370,7 +380,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
             const int item = SH.lv_item[i];
             const int gl = item & 0xFF, jj = item >> 8;
             const LeafEval E = leaf_eval1<G>(SH, gl);
-            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr,
+            backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (AG_TRACE >= 2 && dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 128 + 8 : nullptr,
                            SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
                            SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
           }
@@ -390,20 +400,23 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
       }
       const long long w_d0 = dbg_on ? clock64() - w_t0 : 0;
       named_bar_sync(1, C::THREADS);
-      if (dbg_on && lane == 0) T.dbg[blockIdx.x * 64 + 32 + warp] += w_d0;
+      if (dbg_on && lane == 0) T.dbg[blockIdx.x * 128 + 32 + warp] += w_d0;
       if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[2] += c - t_mark; t_mark = c; }
     }
     // descent of this rollout; its path nodes are listed as the items of the next pool (parity k)
     SH.lv_cnt = s_lvcnt + (k & 1);
     const long long w_t1 = dbg_on ? clock64() : 0;                      // development trace: per-warp time in the descent
-    if (dbg_on && has_game && lane == 0 && s_next[2] != s_next[3]) T.dbg[blockIdx.x * 64 + 7] += 1;   // a descent started while a pool unit was still running
-    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 64 + 8 : nullptr);
+    if (dbg_on && has_game && lane == 0 && s_next[2] != s_next[3]) T.dbg[blockIdx.x * 128 + 7] += 1;   // a descent started while a pool unit was still running
+    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (AG_TRACE >= 2 && dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 128 + 8 : nullptr);
     const long long w_d1 = dbg_on ? clock64() - w_t1 : 0;
     named_bar_sync(1, C::THREADS);
-    if (dbg_on && lane == 0) T.dbg[blockIdx.x * 64 + 48 + warp] += w_d1;
+    if (dbg_on && lane == 0) T.dbg[blockIdx.x * 128 + 48 + warp] += w_d1;
     if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
+    const bool obs = AG_TRACE >= 2 && dbg_on && threadIdx.x == 256;    // development trace: a non-issuing warp's view of the network phase
+    long long ob0 = 0;
+    if (obs) ob0 = clock_after_barrier(s_next);
     {
       // A operand of the base layer (decoder, mcts_gpu.jl:202-223): this thread's operand columns of its row
       u64 x0 = 0, x1 = 0;
@@ -433,13 +446,14 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     if (t < ntiles) {                                                  // an idle tile rejoins at the end-of-rollout barrier
       fence_proxy_async();
       named_bar_sync(NT == 1 ? 2 : 2 + t, 32 * WPT);   // (a compile-time barrier id where there is one tile)
+      if (obs) { const long long c = clock_after_barrier(s_next); T.dbg[blockIdx.x * 128 + 64] += c - ob0; ob0 = c; }
       uint32_t sres[16];                                               // this thread's residual values (swapped orientation)
       for (int l = 0; l < nlayers; l++) {
         const int wll = wl + l;
         const int s = wll % STAGES;
         const bool is_head = (l == nlayers - 1);
         long long lt0 = 0, lt1 = 0, lt2 = 0;
-        const bool ltr = dbg_on && threadIdx.x == 0 && !is_head;
+        const bool ltr = AG_TRACE >= 2 && dbg_on && threadIdx.x == 0 && !is_head;
         if (ltr) lt0 = clock64();
         if (issuer_warp) {
           if (!ts_mode) mbar_wait(bar_full + 8 * s, (wll / STAGES) & 1);
@@ -458,6 +472,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         if (l == 0 && has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
         mbar_wait(bar_done + 8 * t, wll & 1);
         tc_fence_after();
+        if (obs) { const long long c = clock64(); T.dbg[blockIdx.x * 128 + 66 + l] += c - ob0; ob0 = c; }
         long long lt3 = 0;
         if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
         if (!is_head) {
@@ -471,7 +486,9 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           fence_proxy_async();
           long long lt4 = 0;
           if (ltr) { lt4 = clock64(); t_ly[3] += lt4 - lt3; }
+          if (obs) { const long long c = clock64(); T.dbg[blockIdx.x * 128 + 74 + l] += c - ob0; ob0 = c; }
           named_bar_sync(NT == 1 ? 2 : 2 + t, 32 * WPT);   // (a compile-time barrier id where there is one tile)
+          if (obs) { const long long c = clock_after_barrier(s_next); T.dbg[blockIdx.x * 128 + 82 + l] += c - ob0; ob0 = c; }
           if (ltr) t_ly[4] += clock64() - lt4;
         } else {
           // heads: logits = acc + bias, value = σ(acc[A] + bias[A])   (DenseNet.jl:301) -> shared memory (read by the next search phase)
@@ -510,12 +527,13 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     }
     wl += nlayers;
     named_bar_sync(1, C::THREADS);                                     // the outputs are visible to the search phase
+    if (obs) { const long long c = clock_after_barrier(s_next); T.dbg[blockIdx.x * 128 + 65] += c - ob0; }
     if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[4] += c - t_mark; t_mark = c; }
   }
   if (dbg_on && threadIdx.x == 0) {
-    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 64 + i] = t_ph[i];
-    T.dbg[blockIdx.x * 64 + 5] = count; T.dbg[blockIdx.x * 64 + 6] = visits;
-    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 64 + 24 + i] = t_ly[i];
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 128 + i] = t_ph[i];
+    T.dbg[blockIdx.x * 128 + 5] = count; T.dbg[blockIdx.x * 128 + 6] = visits;
+    for (int i = 0; i < 5; i++) T.dbg[blockIdx.x * 128 + 24 + i] = t_ly[i];
   }
 
   // expand + backUp of the last rollout (publishes nothing new for the root: policy_final was written by its descent)
