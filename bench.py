@@ -85,6 +85,27 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def kernel_src_sha16():
+    """sha256 over alphagpu_b200/csrc/* (names + contents): the stamp profiles/ncu_dominant_kernel.json carries."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "alphagpu_b200", "csrc", "*"))):
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def survey_bytes_per_sim(A, S, VS, dbar):
+    """B_sim = d̄·B_node + B_expand + B_io + 16·d̄ — the per-unit figure the roofline contract asks for
+    (988 B at Connect4's d̄ = 3.66)."""
+    b_node = 12 * A + 2 * A + 8
+    b_expand = 2 * S + 8 + 4 * A + 10 * A
+    b_io = 2 * (2 * VS * 2) + 2 * 4 * (A + 1)
+    return dbar * b_node + b_expand + b_io + 16 * dbar
+
+
 def algorithmic_bytes_per_sim(A, S, dbar):
     """SURVEY.md §8(d) / BASELINE.md §3, split by kernel.  A actions, S packed state bytes, dbar expanded nodes per descent."""
     b_node = 12 * A + 2 * A + 8
@@ -152,7 +173,8 @@ def run_extra_config(cfg, ag, torch, parallel, rank, world, local_rank, nn_mode,
            "e2e": {"value": e2e_sims / e2e_wall, "unit": "sims/s", "h2d_bytes_per_step": net.nbytes, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_wall},
            "kernel_ms": {kk: round(v["ms"], 3) for kk, v in classes.items()}}
     if search_ms > 0:
-        bytes_sim = per_sim["select"] + per_sim["expand_backup"]
+        A_ = spec.maxActions                                          # SURVEY.md §8(d) without the network's operands: d̄·B_node + B_expand + 16·d̄
+        bytes_sim = dbar * (14 * A_ + 8) + (2 * cfg["S"] + 8 + 14 * A_) + 16 * dbar
         ach = bytes_sim * pst["sims"] / (search_ms * 1e-3) / 1e9
         out["roofline"] = {"kernel": "search kernels (step = expand + backUp + descent)", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                            "traffic": None, "peak_source": peak_src, "bytes_per_sim": bytes_sim, "share_of_step": search_ms / total_ms}
@@ -381,7 +403,7 @@ def main():
     if fused:
         # one persistent kernel per ply runs the whole rollout loop (search phases + tcgen05 chain): both rooflines refer to its duration
         dom, dom_ms = "ply_fused", classes["ply_fused"]["ms"]
-        bytes_sim = per_sim["select"] + per_sim["expand_backup"] + per_sim["nn"]
+        bytes_sim = survey_bytes_per_sim(spec.maxActions, S, spec.VectorizedState, dbar)
         nn_ms, nn_name = dom_ms, "ply_fused (tcgen05 chain inside the per-ply kernel)"
     else:
         dom = max(("select", "expand_backup"), key=lambda k: classes.get(k, {"ms": 0})["ms"])
@@ -389,11 +411,16 @@ def main():
         bytes_sim = per_sim[dom] + (per_sim["expand_backup"] if dom == "select" else 0)   # the step kernel fuses expand+backup into select
         nn_ms, nn_name = classes["nn"]["ms"], "nn (tcgen05 chain)"
     achieved = bytes_sim * pst["sims"] / (dom_ms * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_note = None, "no ncu capture on file"
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_dominant_kernel.json")) as f:
-            per = json.load(f).get(dom, {}).get("dram_bytes_per_sim")        # ncu --set full capture of one launch, scaled to the average launch
+            cap = json.load(f)
+        if cap.get("kernel_src_sha16") != kernel_src_sha16():
+            traffic_note = "stale: profiles/ncu_dominant_kernel.json was captured on other kernel sources (kernel_src_sha16 differs)"
+        else:
+            per = cap.get(dom, {}).get("dram_bytes_per_sim")                  # ncu --set full capture of one launch, scaled to the average launch
             traffic = None if per is None else per * pst["sims"] / classes[dom]["launches"]
+            traffic_note = "ncu --set full capture of a full-load launch (profiles/ncu_dominant_kernel.json), bytes per sim x sims per average launch"
     except Exception:
         pass
     nn_tf = f_sim * pst["sims"] / (nn_ms * 1e-3) / 1e12
@@ -411,13 +438,15 @@ def main():
         "e2e": {"value": e2e_sims / e2e_wall, "unit": "sims/s", "h2d_bytes_per_step": h2d // args.steps // world, "d2h_bytes_per_step": d2h // args.steps // world,
                 "ms_per_step": 1e3 * e2e_wall / args.steps},
         "gpu_launches": launches,
-        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+        "roofline": {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic, "traffic_source": traffic_note,
                      "peak_source": peak_src, "bytes_per_sim": bytes_sim, "avg_launch_us": 1e3 * dom_ms / classes[dom]["launches"],
                      "share_of_step": dom_ms / total_ms, "sims_per_launch": pst["sims"] / classes[dom]["launches"],
-                     "note": "latency-bound, not HBM-bound: see DESIGN.md §6b and profiles/ncu_dominant_kernel.json (full-L launch: DRAM throughput 7 % of peak, "
-                             "issue slots 30 % busy, 27 of 32 lanes active, L2 hit rate 73 %, stalls on the phase barriers and the global-load scoreboard); 54 % of a "
-                             "generation is spent in plies with more than 128 games per SM, bound by what the games of an SM share, 43.5 % in the tail, where a rollout "
-                             "is a dependent chain — descent round trips, the Newton solve, 8 dependent MMA layers — whose length does not shrink with the number of live games"},
+                     "bytes_per_sim_basis": "SURVEY.md §8(d) B_sim at the measured d_bar (leaf operands and network outputs counted as HBM traffic although the "
+                                            "per-ply kernel keeps them on chip: %d B/sim without them)" % round(per_sim["select"] + per_sim["expand_backup"] + per_sim["nn"]),
+                     "note": "not HBM-bound: see DESIGN.md §6 and profiles/ncu_dominant_kernel.json (full-load launch: issue slots 40 % busy, tensor pipe 11 %, "
+                             "DRAM 736 B per simulation; the search phases are bound by the SM's load/store pipe (one request per lane and 16 bytes), the network "
+                             "phase by epilogue issue slots and tcgen05.mma issue; ~60 % of a generation is spent in plies with more than 128 games per SM, ~37 % in "
+                             "the tail, where a rollout is a dependent chain whose length does not shrink with the number of live games"},
         "roofline_nn": {"kernel": nn_name, "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
                         "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
