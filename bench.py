@@ -322,6 +322,8 @@ def main():
             strong = {"workload": WORKLOAD, "total_games": GAMES, "games_per_gpu": gl, "value": ssims / (sms * 1e-3), "unit": "sims/s", "ms_per_generation": sms,
                       "scaling": "strong"}
             # one generation end to end INCLUDING the sample gather over the ranks (NCCL all_gather of the padded blocks when world > 1)
+            if world > 1:                                                        # communicator set-up and allocator warm-up are not part of a generation
+                parallel.gather_samples({kk: bufs[kk][:1024] for kk in ("state", "policy", "player", "value", "fstate")}, device="cuda")
             sync()
             t0g = time.perf_counter()
             ctx.set_weights(net)
