@@ -54,6 +54,10 @@ constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 #ifndef AG_LANES_SHIFT
 #define AG_LANES_SHIFT 0
 #endif
+// lanes per game where A > 32 (the descent there is bound by issue slots: the ordered sums are executed once per group, not per lane)
+#ifndef AG_LANES_BIG
+#define AG_LANES_BIG 32
+#endif
 // resident 256-thread blocks per SM the search kernels are compiled for (register cap = 65536 / (256 * AG_MINBLOCKS))
 #ifndef AG_MINBLOCKS
 #define AG_MINBLOCKS 4
@@ -61,7 +65,7 @@ constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 template <class G>
 struct Layout {
   static constexpr int A = G::A;
-  static constexpr int W0 = pow2ceil(A) < 32 ? pow2ceil(A) : 32;
+  static constexpr int W0 = pow2ceil(A) < 32 ? pow2ceil(A) : (A > 32 ? AG_LANES_BIG : 32);
   static constexpr int W = (A <= 32 && (W0 >> AG_LANES_SHIFT) >= 1) ? (W0 >> AG_LANES_SHIFT) : W0;   // lanes per game
   static constexpr int APL = (A + W - 1) / W;                      // actions per lane
   static constexpr int APAD = (W * APL + 7) / 8 * 8;
@@ -365,9 +369,17 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
 // ------------------------------------------------------------------------------------------------
 // select: kdescendTree! (mcts_gpu.jl:100-199).  One group of W lanes per game.
 // ------------------------------------------------------------------------------------------------
+// Large action sets: the ORDERED sums of a level (Newton sums over the children in creation order, the inverse-CDF scan and
+// prior_rem in ascending action order) are the same dependent chain on every lane of the group, so their cost is issue slots, not
+// latency: the addends are staged in a per-group shared-memory scratch and read back four (two pairs) per broadcast LDS.128, which
+// leaves ~1.5 instructions per addend instead of a shuffle + select + add on every lane.
+template <class G> struct SelScratch {
+  static constexpr int FLOATS = Layout<G>::FAST ? 4 : 2 * Layout<G>::W * Layout<G>::APL;   // per game: (t1, t2) pairs of every child slot
+  static constexpr int A4 = (G::A + 3) / 4 * 4;
+};
 template <class G>
 AG_D void select_game(const SearchParams& P, const int g, const int l, const unsigned gm, int L, int rollout, int last_rollout, float cpuct,
-                      const float* __restrict__ prob, u64 seed, u32 ply) {
+                      const float* __restrict__ prob, u64 seed, u32 ply, float* __restrict__ sc) {
   typedef Layout<G> Lay;
   constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
   char* gbase = P.tree + (size_t)g * P.game_stride;
@@ -416,65 +428,69 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
         if (j * W + l < A) alpha = fmaxf(alpha, fadd(q[j], fmaxf(top[j], 1e-4f)));
       }
       alpha = gmax<W>(gm, alpha);
-      // The Newton sums run over the CHILDREN only, in creation (slot) order: lane l gathers the statistics of the children in slots
-      // l, l + W, … once, so that an iteration costs two divisions per lane and slot group instead of two per lane and action group.
+      // The Newton sums run over the CHILDREN only, in creation (slot) order: lane l owns the children in slots l, l + W, … and reads
+      // their statistics once (the record's q / prior lines were just loaded), so that an iteration costs two divisions per lane and
+      // slot group instead of two per lane and action group.
       const int nchild = h.nchild;
-      const int ngroups = (nchild + W - 1) / W;                                      // warp-uniform, <= APL
+      const int ngroups = (nchild + W - 1) / W;                                      // group-uniform, <= APL
       float ctop[APL], cq[APL];
 #pragma unroll
       for (int j = 0; j < APL; j++) {
-        ctop[j] = 0.f; cq[j] = 0.f;
-        if (j < ngroups) {
-          const int a = (j * W + l < nchild) ? ord[j] - 1 : 0;
-          const int srcl = a % W, srci = a / W;
-#pragma unroll
-          for (int jj = 0; jj < APL; jj++) {
-            const float vq = gshfl<W>(gm, q[jj], srcl), vt = gshfl<W>(gm, top[jj], srcl);
-            if (srci == jj) { cq[j] = vq; ctop[j] = vt; }
-          }
+        ctop[j] = 0.f; cq[j] = 0.f;                                                  // an empty slot contributes +0 to both sums
+        if (j * W + l < nchild) {
+          const int a = ord[j] - 1;
+          cq[j] = *reinterpret_cast<const float*>(rec + Lay::OFF_Q + 4 * a);
+          ctop[j] = fmul(lambda, *reinterpret_cast<const float*>(rec + Lay::OFF_PRIOR + 4 * a));
         }
       }
       // Divisions: the branch-free fast path (common.cuh: fdiv_fast — correctly rounded inside its operand box, checked against
       // __fdiv_rn on 2^34 pairs) whenever every operand of every lane is in the box, else the IEEE division; same quotients either way.
-      // The derivative is accumulated with all signs flipped (G = -gs: rounding is sign-symmetric), so every numerator is >= 0.
-      bool num_ok = fdiv_box_num(rem);
+      // A denominator b that is also squared is held to [2^-30, 2^30], which puts b*b in the box as well.  The numerators of the child
+      // terms are a subset of top[].  The derivative is accumulated with all signs flipped (G = -gs: rounding is sign-symmetric), so
+      // every numerator is >= 0.
+      bool num_ok = fdiv_box_num_bits(rem);
 #pragma unroll
-      for (int j = 0; j < APL; j++) num_ok = num_ok && fdiv_box_num(ctop[j]) && fdiv_box_num(top[j]);
+      for (int j = 0; j < APL; j++) num_ok = num_ok && fdiv_box_num_bits(top[j]);
       num_ok = __all_sync(gm, num_ok);
+      float2* sc2 = reinterpret_cast<float2*>(sc);
+      const float4* sc4 = reinterpret_cast<const float4*>(sc);
+      const f32x2 one2 = pack2f(1.0f, 1.0f);
       float err = __int_as_float(0x7f800000);
       for (int it = 0; it < 100; it++) {                                             // :141-162
         const float a2 = fmul(alpha, alpha);
         float bot[APL], bot2[APL];
-        bool ok = num_ok && fdiv_box_den(alpha) && fdiv_box_den(a2);
+        bool ok = num_ok && fdiv_box_den_sq(alpha);
 #pragma unroll
         for (int j = 0; j < APL; j++) {
           bot[j] = fsub(alpha, cq[j]); bot2[j] = fmul(bot[j], bot[j]);
-          if (j < ngroups) ok = ok && fdiv_box_den(bot[j]) && fdiv_box_den(bot2[j]);
+          if (j < ngroups) ok = ok && fdiv_box_den_sq(bot[j]);
         }
         ok = __all_sync(gm, ok);
         float S, G;
-        float t1[APL], t2[APL];
         if (ok) {
           S = fdiv_fast(rem, alpha);
           G = fdiv_fast(rem, a2);
 #pragma unroll
-          for (int j = 0; j < APL; j++) {
-            t1[j] = 0.f; t2[j] = 0.f;
-            if (j < ngroups) { t1[j] = fdiv_fast(ctop[j], bot[j]); t2[j] = fdiv_fast(ctop[j], bot2[j]); }
-          }
+          for (int j = 0; j < APL; j++)
+            if (j < ngroups) sc2[j * W + l] = make_float2(fdiv_fast(ctop[j], bot[j]), fdiv_fast(ctop[j], bot2[j]));
         } else {
           S = fdiv(rem, alpha);
           G = fdiv(rem, a2);
 #pragma unroll
-          for (int j = 0; j < APL; j++) {
-            t1[j] = 0.f; t2[j] = 0.f;
-            if (j < ngroups) { t1[j] = fdiv(ctop[j], bot[j]); t2[j] = fdiv(ctop[j], bot2[j]); }
-          }
+          for (int j = 0; j < APL; j++)
+            if (j < ngroups) sc2[j * W + l] = make_float2(fdiv(ctop[j], bot[j]), fdiv(ctop[j], bot2[j]));
         }
-        for (int k = 0; k < nchild; k++) {                                           // children in creation (slot) order
-          S = fadd(S, gshfl<W>(gm, pick<APL>(t1, k / W), k % W));
-          G = fadd(G, gshfl<W>(gm, pick<APL>(t2, k / W), k % W));
+        __syncwarp(gm);
+        // children in creation (slot) order, both sums side by side: fma(x, 1, t) is the correctly rounded x + t.  An odd count reads
+        // one empty slot of the same group: + (+0) changes nothing.
+        f32x2 SG = pack2f(S, G);
+        for (int k = 0; k < nchild; k += 2) {
+          const float4 v = sc4[k >> 1];
+          SG = fma2(SG, one2, pack2f(v.x, v.y));
+          SG = fma2(SG, one2, pack2f(v.z, v.w));
         }
+        unpack2f(SG, S, G);
+        __syncwarp(gm);                                                              // the scratch is rewritten by the next iteration / the scan
         const float newerr = fsub(S, 1.f);
         if (newerr < 0.001f || newerr == err) break;
         // α - err/gs with gs = -G
@@ -485,7 +501,7 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
         float den[APL];
         bool ok = num_ok;
 #pragma unroll
-        for (int j = 0; j < APL; j++) { den[j] = fsub(alpha, q[j]); ok = ok && fdiv_box_den(den[j]); }
+        for (int j = 0; j < APL; j++) { den[j] = fsub(alpha, q[j]); ok = ok && fdiv_box_den_bits(den[j]); }
         ok = __all_sync(gm, ok);
 #pragma unroll
         for (int j = 0; j < APL; j++) pol[j] = ok ? fdiv_fast(top[j], den[j]) : fdiv(top[j], den[j]);      // :165-169
@@ -509,27 +525,48 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
       const int w = depth & 3;
       u = u01(w == 0 ? rnd.v[0] : w == 1 ? rnd.v[1] : w == 2 ? rnd.v[2] : rnd.v[3]);
     }
-    // inverse-CDF scan in ascending action order (:172-182)
-    float cum = 0.f;
+    // inverse-CDF scan in ascending action order (:172-182): the sample is the last action with π̄ > 0 at or before the first
+    // index whose running sum reaches u
     int best = -1;
-    bool done = false;                                                                // the same on every lane of the group
+    if constexpr (Lay::FAST) {
+      float cum = 0.f;
+      bool done = false;                                                              // the same on every lane of the group
 #pragma unroll
-    for (int j = 0; j < APL; j++) {
-#pragma unroll
-      for (int s8 = 0; s8 < W; s8 += 8) {
-        if (!done) {                                                                  // the rest of the scan changes nothing once the sample is found
-#pragma unroll
-          for (int s = s8; s < s8 + 8 && s < W; s++) {
-            if (j * W + s < A) {
-              const float d = gshfl<W>(gm, pol[j], s);
-              if (!done) {
-                cum = fadd(cum, d);
-                if (d > 0.f) best = j * W + s;
-                if (cum >= u) done = true;
-              }
-            }
+      for (int s = 0; s < W; s++) {
+        if (s < A) {
+          const float d = gshfl<W>(gm, pol[0], s);
+          if (!done) {
+            cum = fadd(cum, d);
+            if (d > 0.f) best = s;
+            if (cum >= u) done = true;
           }
         }
+      }
+    } else {
+      constexpr int A4 = SelScratch<G>::A4;
+#pragma unroll
+      for (int j = 0; j < APL; j++) sc[j * W + l] = (j * W + l < A) ? pol[j] : 0.f;
+      __syncwarp(gm);
+      const float4* sc4 = reinterpret_cast<const float4*>(sc);
+      float cum = 0.f;
+      int kstar = 0;                                                                  // number of leading indices with sum < u
+      bool open = true;
+#pragma unroll
+      for (int k = 0; k < A4; k += 4) {
+        if ((k & 7) == 0 && k > 0 && !open) break;                                    // the rest of the scan changes nothing
+        const float4 v = sc4[k >> 2];
+        cum = fadd(cum, v.x); open = open && !(cum >= u); kstar += open ? 1 : 0;
+        cum = fadd(cum, v.y); open = open && !(cum >= u); kstar += open ? 1 : 0;
+        cum = fadd(cum, v.z); open = open && !(cum >= u); kstar += open ? 1 : 0;
+        cum = fadd(cum, v.w); open = open && !(cum >= u); kstar += open ? 1 : 0;
+      }
+      __syncwarp(gm);
+      const int lane0 = (int)(threadIdx.x & 31) - l;                                  // first lane of the group inside its warp
+#pragma unroll
+      for (int j = 0; j < APL; j++) {
+        const int a = j * W + l;
+        const unsigned b = __ballot_sync(gm, a < A && a <= kstar && pol[j] > 0.f) & gm;
+        if (b) best = j * W + (31 - __clz(b)) - lane0;
       }
     }
     if (best < 0) best = 0;
@@ -537,7 +574,9 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
       P.path_node[(size_t)g * P.R + depth] = (uint8_t)node;
       P.path_move[(size_t)g * P.R + depth] = (uint8_t)best;
     }
-    int c = gshfl<W>(gm, pick<APL>(ch, best / W), best % W);
+    int c;
+    if constexpr (Lay::FAST) c = gshfl<W>(gm, ch[0], best);
+    else c = (int)*reinterpret_cast<const uint8_t*>(rec + Lay::OFF_CHILD + best);      // (the line was loaded at the top of the level)
     if (c == 0) {                                                                     // allocate the child (:183-191)
       nn += 1;
       c = nn;
@@ -556,13 +595,16 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
       }
       if constexpr (!Lay::FAST) {
         // prior_rem of the parent now excludes the new child: the same ascending sum over the actions that still have none
+        constexpr int A4 = SelScratch<G>::A4;
+#pragma unroll
+        for (int j = 0; j < APL; j++) sc[j * W + l] = (j * W + l < A && ch[j] == 0 && j * W + l != best) ? p[j] : 0.f;
+        __syncwarp(gm);
+        const float4* sc4 = reinterpret_cast<const float4*>(sc);
         float rem = 0.f;
 #pragma unroll
-        for (int j = 0; j < APL; j++) {
-          const float contrib = (ch[j] == 0 && j * W + l != best) ? p[j] : 0.f;
-#pragma unroll
-          for (int s = 0; s < W; s++)
-            if (j * W + s < A) rem = fadd(rem, gshfl<W>(gm, contrib, s));
+        for (int k = 0; k < A4; k += 4) {
+          const float4 v = sc4[k >> 2];
+          rem = fadd(fadd(fadd(fadd(rem, v.x), v.y), v.z), v.w);
         }
         if (l == 0) {
           reinterpret_cast<NodeAux*>(rec + Lay::OFF_AUX)->rem = rem;
@@ -594,9 +636,11 @@ template <class G>
 __global__ void __launch_bounds__(256, AG_MINBLOCKS) select_kernel(SearchParams P, int L, int rollout, int last_rollout, float cpuct,
                                                      const float* __restrict__ prob, u64 seed, u32 ply) {
   constexpr int W = Layout<G>::W;
+  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   if (g >= L) return;
-  select_game<G>(P, g, threadIdx.x & (W - 1), group_mask<W>(), L, rollout, last_rollout, cpuct, prob, seed, ply);
+  select_game<G>(P, g, threadIdx.x & (W - 1), group_mask<W>(), L, rollout, last_rollout, cpuct, prob, seed, ply,
+                 s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1151,27 +1195,31 @@ template <class G>
 __global__ void __launch_bounds__(256, AG_MINBLOCKS) step_kernel(SearchParams P, int L, int rollout, int last_rollout, int training, float cpuct, u64 seed,
                                                    u32 ply) {
   constexpr int W = Layout<G>::W;
+  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   if (g >= L) return;
   const int l = threadIdx.x & (W - 1);
   const unsigned gm = group_mask<W>();
   expand_backup_game<G, false>(P, g, l, gm, training, 0, nullptr, nullptr, cpuct);
   __syncwarp(gm);                                      // the group's global writes (q, visits, prior, flags) are ordered before its reads
-  select_game<G>(P, g, l, gm, L, rollout, last_rollout, cpuct, nullptr, seed, ply);
+  select_game<G>(P, g, l, gm, L, rollout, last_rollout, cpuct, nullptr, seed, ply, s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 
 // ---- the same three launches, addressed through a SegParams record (graph replay, one stream per slice) ----
 template <class G>
 __global__ void __launch_bounds__(256, AG_MINBLOCKS) select_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
   constexpr int W = Layout<G>::W;
+  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
   const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   const SegParams S = *sp;
   if (gl >= S.len) return;
-  select_game<G>(P, S.off + gl, threadIdx.x & (W - 1), group_mask<W>(), 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply);
+  select_game<G>(P, S.off + gl, threadIdx.x & (W - 1), group_mask<W>(), 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply,
+                 s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 template <class G>
 __global__ void __launch_bounds__(256, AG_MINBLOCKS) step_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
   constexpr int W = Layout<G>::W;
+  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
   const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   const SegParams S = *sp;
   if (gl >= S.len) return;
@@ -1179,7 +1227,7 @@ __global__ void __launch_bounds__(256, AG_MINBLOCKS) step_seg_kernel(SearchParam
   const unsigned gm = group_mask<W>();
   expand_backup_game<G, false>(P, g, l, gm, S.training, 0, nullptr, nullptr, S.cpuct);
   __syncwarp(gm);
-  select_game<G>(P, g, l, gm, 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply);
+  select_game<G>(P, g, l, gm, 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply, s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 template <class G>
 __global__ void __launch_bounds__(256) expand_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int last_rollout) {
