@@ -322,7 +322,7 @@ struct EngineT : EngineBase {
 
   bool is_tc() const { return cfg.nn_mode == AGPU_NN_BF16_TC || cfg.nn_mode == AGPU_NN_FP16_TC; }
   int tc_fmt() const { return cfg.nn_mode == AGPU_NN_FP16_TC ? 1 : 0; }
-  static int blocks_for_groups(int64_t L) { return (int)((L * Lay::W + 255) / 256); }
+  static int blocks_for_groups(int64_t L) { return (int)((L * Lay::W + Lay::SB - 1) / Lay::SB); }
   static int blocks_for_threads(int64_t n) { return (int)((n + 255) / 256); }
 
   NNInput nn_input_tree() const {
@@ -399,10 +399,10 @@ struct EngineT : EngineBase {
     cudaError_t e = cudaSuccess;
     for (int k = 0; k < visits && e == cudaSuccess; k++) {
       const int last = (k == visits - 1);
-      if (k == 0) select_seg_kernel<G><<<gb, 256, 0, st>>>(P, sp, 0, last);
-      else step_seg_kernel<G><<<gb, 256, 0, st>>>(P, sp, k, last);
+      if (k == 0) select_seg_kernel<G><<<gb, Lay::SB, 0, st>>>(P, sp, 0, last);
+      else step_seg_kernel<G><<<gb, Lay::SB, 0, st>>>(P, sp, k, last);
       e = nn_on(st, slot, I, seg_cap, nn_out.p, Lay::OUTS);
-      if (last) expand_seg_kernel<G><<<gb, 256, 0, st>>>(P, sp, 1);
+      if (last) expand_seg_kernel<G><<<gb, Lay::SB, 0, st>>>(P, sp, 1);
     }
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = cudaStreamEndCapture(st, &graph);
@@ -553,16 +553,16 @@ struct EngineT : EngineBase {
 
   void launch_select(int64_t L, int rollout, int last, float cpuct, const float* dprob, uint64_t seed, uint32_t ply) {
     last_cpuct = cpuct;
-    launch(K_SELECT, [&] { select_kernel<G><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, rollout, last, cpuct, dprob, seed, ply); });
+    launch(K_SELECT, [&] { select_kernel<G><<<blocks_for_groups(L), Lay::SB, 0, stream>>>(P, (int)L, rollout, last, cpuct, dprob, seed, ply); });
   }
   void launch_expand(int64_t L, int training, int last, const float* dprior, const float* dvalue) {
-    if (dprior) launch(K_EXPAND, [&] { expand_backup_kernel<G, true><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, training, last, dprior, dvalue, last_cpuct); });
-    else launch(K_EXPAND, [&] { expand_backup_kernel<G, false><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, training, last, nullptr, nullptr, last_cpuct); });
+    if (dprior) launch(K_EXPAND, [&] { expand_backup_kernel<G, true><<<blocks_for_groups(L), Lay::SB, 0, stream>>>(P, (int)L, training, last, dprior, dvalue, last_cpuct); });
+    else launch(K_EXPAND, [&] { expand_backup_kernel<G, false><<<blocks_for_groups(L), Lay::SB, 0, stream>>>(P, (int)L, training, last, nullptr, nullptr, last_cpuct); });
   }
 
   void launch_step(int64_t L, int rollout, int last, int training, float cpuct, uint64_t seed, uint32_t ply) {
     last_cpuct = cpuct;
-    launch(K_SELECT, [&] { step_kernel<G><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, rollout, last, training, cpuct, seed, ply); });
+    launch(K_SELECT, [&] { step_kernel<G><<<blocks_for_groups(L), Lay::SB, 0, stream>>>(P, (int)L, rollout, last, training, cpuct, seed, ply); });
   }
 
   // the rollout loop of mcts_single (mcts_gpu.jl:396-439), no host synchronisation inside.  With the in-kernel RNG the
@@ -632,7 +632,7 @@ struct EngineT : EngineBase {
     }
     // the kernel indexes prob by (rollout*L + g): pass rollout 0 for the slice, keep the RNG counter separately
     last_cpuct = cpuct;
-    if (dprob) launch(K_SELECT, [&] { select_kernel<G><<<blocks_for_groups(L), 256, 0, stream>>>(P, (int)L, 0, last, cpuct, dprob, seed, ply); });
+    if (dprob) launch(K_SELECT, [&] { select_kernel<G><<<blocks_for_groups(L), Lay::SB, 0, stream>>>(P, (int)L, 0, last, cpuct, dprob, seed, ply); });
     else launch_select(L, rollout, last, cpuct, nullptr, seed, ply);
     AG_CK(cudaGetLastError());
     AG_CK(cudaStreamSynchronize(stream));

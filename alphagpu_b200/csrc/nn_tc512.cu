@@ -30,6 +30,12 @@ constexpr int W5_STAGES = 5;
 constexpr int W5_CHUNK = 128 * 128;                   // 16 KB: 128 outputs x 64 K operands
 constexpr int W5_A_BYTES = 128 * W5_N * 2;            // 128 KB
 constexpr int W5_THREADS = 32 * 18;
+// register cap: what the 576 threads leave of the register file decides how many blocks of the search kernels (128 threads x 64
+// registers) can share the SM with a network CTA — their descents fill the issue slots this tensor-bound kernel leaves idle
+#ifndef AG_W5_MAXREG
+#define AG_W5_MAXREG 112
+#endif
+constexpr int W5_MAXREG = AG_W5_MAXREG;
 constexpr int W5_SMEM = W5_A_BYTES + W5_STAGES * W5_CHUNK + 1024 + 1024;
 
 struct Tc512Args {
@@ -57,7 +63,7 @@ template <int FMT> AG_D float2 unpack2(uint32_t u) {
 }
 
 template <int FMT>
-__global__ void __launch_bounds__(W5_THREADS, 1) tc_mlp512_kernel(Tc512Args T, NNInput I, int L, float* __restrict__ out, int outs) {
+__global__ void __maxnreg__(W5_MAXREG) tc_mlp512_kernel(Tc512Args T, NNInput I, int L, float* __restrict__ out, int outs) {
   int seg_off = 0;
   if (I.seg) {
     seg_off = I.seg[0];
@@ -194,23 +200,27 @@ __global__ void __launch_bounds__(W5_THREADS, 1) tc_mlp512_kernel(Tc512Args T, N
       mbar_wait(bar_done, l & 1);
       tc_fence_after();
       if (l < last_layer) {
-        // b = relu(acc) (base) or round16(b + relu(acc)); the activation tile is overwritten in place (all MMAs of the layer are done)
-#pragma unroll 1
+        // b = relu(acc) (base) or round16(b + relu(acc)); the activation tile is overwritten in place (all MMAs of the layer are done).
+        // The tensor-memory load of chunk cb + 1 is in flight while chunk cb is processed (tcgen05.wait::ld waits for ALL outstanding
+        // loads: without the double buffer the load latency is exposed eight times per layer).
+        uint32_t v[2][16];
+        tmem_ld16(tmem_row, v[0]);
+#pragma unroll
         for (int cb = 0; cb < 8; cb++) {
-          uint32_t v[16];
-          tmem_ld16(tmem_row + 16 * cb, v);
-          uint4 old0 = make_uint4(0, 0, 0, 0), old1 = make_uint4(0, 0, 0, 0);
+          const int b = cb & 1;
           unsigned char* p0 = chunk_ptr(16 * cs + 2 * cb);
           unsigned char* p1 = chunk_ptr(16 * cs + 2 * cb + 1);
+          uint4 old0 = make_uint4(0, 0, 0, 0), old1 = make_uint4(0, 0, 0, 0);
           if (l > 0) { old0 = *reinterpret_cast<const uint4*>(p0); old1 = *reinterpret_cast<const uint4*>(p1); }
-          tmem_ld_wait();
+          tmem_ld_wait();                                              // chunk cb has arrived
+          if (cb + 1 < 8) tmem_ld16(tmem_row + 16 * (cb + 1), v[b ^ 1]);
           const uint32_t ow[8] = {old0.x, old0.y, old0.z, old0.w, old1.x, old1.y, old1.z, old1.w};
           uint32_t nw[8];
 #pragma unroll
           for (int e = 0; e < 8; e++) {
             const float2 o = unpack2<FMT>(ow[e]);
-            const float h0 = o.x + fmaxf(__uint_as_float(v[2 * e]), 0.f);
-            const float h1 = o.y + fmaxf(__uint_as_float(v[2 * e + 1]), 0.f);
+            const float h0 = o.x + fmaxf(__uint_as_float(v[b][2 * e]), 0.f);
+            const float h1 = o.y + fmaxf(__uint_as_float(v[b][2 * e + 1]), 0.f);
             nw[e] = pack2<FMT>(h0, h1);
           }
           *reinterpret_cast<uint4*>(p0) = make_uint4(nw[0], nw[1], nw[2], nw[3]);

@@ -62,6 +62,10 @@ constexpr int pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 #ifndef AG_MINBLOCKS
 #define AG_MINBLOCKS 4
 #endif
+// threads per block of the search kernels for large action sets (a block's slot is held until its slowest game ends its descent)
+#ifndef AG_BLOCK_BIG
+#define AG_BLOCK_BIG 128
+#endif
 template <class G>
 struct Layout {
   static constexpr int A = G::A;
@@ -75,6 +79,8 @@ struct Layout {
   // a node's statistics change only when a backup passes through it (sticky `uptodate`, mcts_gpu.jl:114,321) and the solve is a
   // pure function of them.  Large action sets keep the cooperative solve-at-descent (the network dominates there).
   static constexpr bool FAST = (A <= 9);
+  static constexpr int SB = FAST ? 256 : AG_BLOCK_BIG;            // threads per block of select / expand+backup / step kernels
+  static constexpr int SB_MIN = AG_MINBLOCKS * 256 / SB;          // resident blocks per SM they are compiled for
   static constexpr int a16(int x) { return (x + 15) / 16 * 16; }
   // FAST record: what the descent reads (header, child ids, π̄) sits in the first 64 bytes, so one 64-byte-aligned sector pair
   // serves a level of the descent; the backup's lane reads the rest.  Other layouts: prior | q | visits | child | order | state | header.
@@ -377,6 +383,16 @@ template <class G> struct SelScratch {
   static constexpr int FLOATS = Layout<G>::FAST ? 4 : 2 * Layout<G>::W * Layout<G>::APL;   // per game: (t1, t2) pairs of every child slot
   static constexpr int A4 = (G::A + 3) / 4 * 4;
 };
+// ascending-index fp32 sum of n4 (a multiple of 4) staged addends, continued from acc
+AG_D float ordered_sum4(const float* __restrict__ sc, const int n4, float acc) {
+  const float4* sc4 = reinterpret_cast<const float4*>(sc);
+#pragma unroll
+  for (int k = 0; k < n4; k += 4) {
+    const float4 v = sc4[k >> 2];
+    acc = fadd(fadd(fadd(fadd(acc, v.x), v.y), v.z), v.w);
+  }
+  return acc;
+}
 template <class G>
 AG_D void select_game(const SearchParams& P, const int g, const int l, const unsigned gm, int L, int rollout, int last_rollout, float cpuct,
                       const float* __restrict__ prob, u64 seed, u32 ply, float* __restrict__ sc) {
@@ -570,7 +586,7 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
       }
     }
     if (best < 0) best = 0;
-    if (Lay::FAST && l == 0) {                                                        // remember the path for the lane-parallel backup
+    if (l == 0) {                                                                     // remember the path for the lane-parallel backup
       P.path_node[(size_t)g * P.R + depth] = (uint8_t)node;
       P.path_move[(size_t)g * P.R + depth] = (uint8_t)best;
     }
@@ -599,13 +615,7 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
 #pragma unroll
         for (int j = 0; j < APL; j++) sc[j * W + l] = (j * W + l < A && ch[j] == 0 && j * W + l != best) ? p[j] : 0.f;
         __syncwarp(gm);
-        const float4* sc4 = reinterpret_cast<const float4*>(sc);
-        float rem = 0.f;
-#pragma unroll
-        for (int k = 0; k < A4; k += 4) {
-          const float4 v = sc4[k >> 2];
-          rem = fadd(fadd(fadd(fadd(rem, v.x), v.y), v.z), v.w);
-        }
+        const float rem = ordered_sum4(sc, A4, 0.f);
         if (l == 0) {
           reinterpret_cast<NodeAux*>(rec + Lay::OFF_AUX)->rem = rem;
           hdr_store(nrec + Lay::OFF_AUX, 0ull);
@@ -627,16 +637,16 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
   if (l == 0) {
     P.leaf[g] = node;                                                                  // :195
     P.nnodes[g] = nn;
-    if (Lay::FAST) P.path_len[g] = (uint8_t)depth;
+    P.path_len[g] = (uint8_t)depth;
     if (P.counters) { atomicAdd(&P.counters[0], (unsigned long long)depth); atomicAdd(&P.counters[1], 1ull); }
   }
 }
 
 template <class G>
-__global__ void __launch_bounds__(256, AG_MINBLOCKS) select_kernel(SearchParams P, int L, int rollout, int last_rollout, float cpuct,
+__global__ void __launch_bounds__(Layout<G>::SB, Layout<G>::SB_MIN) select_kernel(SearchParams P, int L, int rollout, int last_rollout, float cpuct,
                                                      const float* __restrict__ prob, u64 seed, u32 ply) {
   constexpr int W = Layout<G>::W;
-  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
+  __shared__ __align__(16) float s_sel[(Layout<G>::SB / W) * SelScratch<G>::FLOATS];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   if (g >= L) return;
   select_game<G>(P, g, threadIdx.x & (W - 1), group_mask<W>(), L, rollout, last_rollout, cpuct, prob, seed, ply,
@@ -657,7 +667,7 @@ struct LeafEval {
 
 template <class G, bool INJECT>
 AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const unsigned gm, int training, int last_rollout,
-                          const float* __restrict__ prior_in, const float* __restrict__ value_in) {
+                          const float* __restrict__ prior_in, const float* __restrict__ value_in, float* __restrict__ sc = nullptr) {
   typedef Layout<G> Lay;
   constexpr int W = Lay::W, APL = Lay::APL, A = G::A, REC = Lay::REC;
   char* gbase = P.tree + (size_t)g * P.game_stride;
@@ -686,8 +696,17 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 #pragma unroll
       for (int j = 0; j < APL; j++) {
         e[j] = (j * W + l < A) ? c_expf(fsub(x[j], m)) : 0.f;
+        if constexpr (Lay::FAST) {
 #pragma unroll
-        for (int s = 0; s < W; s++) if (j * W + s < A) ssum = fadd(ssum, gshfl<W>(gm, e[j], s));
+          for (int s = 0; s < W; s++) if (j * W + s < A) ssum = fadd(ssum, gshfl<W>(gm, e[j], s));
+        } else {
+          sc[j * W + l] = e[j];                                                          // ordered sums: staged (see SelScratch)
+        }
+      }
+      if constexpr (!Lay::FAST) {
+        __syncwarp(gm);
+        ssum = ordered_sum4(sc, SelScratch<G>::A4, 0.f);
+        __syncwarp(gm);
       }
 #pragma unroll
       for (int j = 0; j < APL; j++) pin[j] = fdiv(e[j], ssum);
@@ -702,8 +721,17 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
       legal[j] = a < A && G::can_play(st, a + 1);
       const float contrib = legal[j] ? pin[j] : 0.f;
       acount += gcount<W>(gm, legal[j]);
+      if constexpr (Lay::FAST) {
 #pragma unroll
-      for (int s = 0; s < W; s++) if (j * W + s < A) normalize = fadd(normalize, gshfl<W>(gm, contrib, s));
+        for (int s = 0; s < W; s++) if (j * W + s < A) normalize = fadd(normalize, gshfl<W>(gm, contrib, s));
+      } else {
+        sc[a] = contrib;
+      }
+    }
+    if constexpr (!Lay::FAST) {
+      __syncwarp(gm);
+      normalize = ordered_sum4(sc, SelScratch<G>::A4, 0.f);
+      __syncwarp(gm);
     }
     const bool rootmix = (leaf == 0) && training;                                       // :259-275
     const float unif = fdiv(0.25f, (float)acount);
@@ -721,15 +749,15 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
     if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
     if constexpr (!Lay::FAST) {
       // NodeAux of the freshly expanded node: no child yet, so prior_rem is the ascending sum of the whole prior; #{prior > 0}; no visits
-      float rem = 0.f;
       int pos = 0;
 #pragma unroll
       for (int j = 0; j < APL; j++) {
         pos += gcount<W>(gm, prv[j] > 0.f);
-#pragma unroll
-        for (int s = 0; s < W; s++)
-          if (j * W + s < A) rem = fadd(rem, gshfl<W>(gm, prv[j], s));
+        sc[j * W + l] = prv[j];
       }
+      __syncwarp(gm);
+      const float rem = ordered_sum4(sc, SelScratch<G>::A4, 0.f);
+      __syncwarp(gm);
       if (l == 0) {
         NodeAux ax; ax.rem = rem; ax.acount = (uint16_t)pos; ax.nvis = 0;
         *reinterpret_cast<NodeAux*>(rec + Lay::OFF_AUX) = ax;
@@ -1121,11 +1149,12 @@ AG_D LeafEval leaf_eval1(const RolloutShared<G>& SH, const int gl) {
 
 template <class G, bool INJECT>
 AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, const unsigned gm, int training, int last_rollout,
-                             const float* __restrict__ prior_in, const float* __restrict__ value_in, const float cpuct) {
+                             const float* __restrict__ prior_in, const float* __restrict__ value_in, const float cpuct,
+                             float* __restrict__ sc = nullptr) {
   typedef Layout<G> Lay;
   constexpr int W = Lay::W, REC = Lay::REC;
   char* gbase = P.tree + (size_t)g * P.game_stride;
-  const LeafEval E = expand_game<G, INJECT>(P, g, l, gm, training, last_rollout, prior_in, value_in);
+  const LeafEval E = expand_game<G, INJECT>(P, g, l, gm, training, last_rollout, prior_in, value_in, sc);
   // backUp: :306-328
   if constexpr (Lay::FAST) {
     // lane-parallel: lane jj takes the jj-th node of the recorded path
@@ -1136,80 +1165,72 @@ AG_D void expand_backup_game(const SearchParams& P, const int g, const int l, co
     }
     return;
   }
-  const bool term = E.term != 0;
-  const float v = E.v;
-  int nindex = E.parent;
-  int move = E.action;
-  if (term) {
-    // value = (1 + player*r)/2 is a Float64 in the reference (:314): the running mean on this path is evaluated in double
-    double value = E.value0_d;
-    while (nindex != 0) {
-      char* nrec = gbase + (size_t)(nindex - 1) * REC;
-      if (l == ((move - 1) % W)) {
-        float* qp = reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * (move - 1));
-        uint16_t* vp = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * (move - 1));
-        const float vf = (float)*vp;
-        const float prod = fmul(vf, *qp);
-        const float den = fadd(vf, 1.f);
-        *qp = (float)__ddiv_rn(__dadd_rn((double)prod, __dsub_rn(1.0, value)), (double)den);
-        *vp = (uint16_t)(*vp + 1);
-        uint16_t* nv = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_AUX + 6);            // NodeAux::nvis
-        *nv = (uint16_t)(*nv + 1);
+  // Large action sets: the same lane-parallel walk over the recorded path (one ancestor per lane: the loads of all levels are in
+  // flight together instead of one parent pointer after the other); only the visited action's statistics change here, π̄ is solved
+  // by the next descent.  The value an ancestor receives is the leaf value flipped once per level below it, as that literal chain.
+  const int d = P.path_len[g];
+  for (int base = 0; base < d; base += W) {
+    const int jj = base + l;
+    if (jj < d) {
+      const int nd = P.path_node[(size_t)g * P.R + jj], mv = P.path_move[(size_t)g * P.R + jj];
+      char* nrec = gbase + (size_t)nd * REC;
+      float* qp = reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * mv);
+      uint16_t* vp = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * mv);
+      uint16_t* nv = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_AUX + 6);              // NodeAux::nvis
+      const int vold = *vp, nvold = *nv;
+      const float qold = *qp;
+      const float vf = (float)vold;
+      const int flips = d - 1 - jj;
+      float qnew;
+      if (E.term) {
+        // value = (1 + player*r)/2 is a Float64 in the reference (:314): the running mean on this path is evaluated in double
+        double val = E.value0_d;
+        for (int t = 0; t < flips; t++) val = __dsub_rn(1.0, val);
+        qnew = (float)__ddiv_rn(__dadd_rn((double)fmul(vf, qold), __dsub_rn(1.0, val)), (double)fadd(vf, 1.f));
+      } else {
+        float val = E.v;
+        for (int t = 0; t < flips; t++) val = fsub(1.f, val);                            // :324
+        qnew = fdiv(fadd(fmul(vf, qold), fsub(1.f, val)), fadd(vf, 1.f));               // :319
       }
-      const NodeHdr nh = *reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR);
-      move = nh.action; nindex = nh.parent;
-      value = __dsub_rn(1.0, value);
-    }
-  } else {
-    float value = v;
-    while (nindex != 0) {
-      char* nrec = gbase + (size_t)(nindex - 1) * REC;
-      if (l == ((move - 1) % W)) {
-        float* qp = reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * (move - 1));
-        uint16_t* vp = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * (move - 1));
-        const float vf = (float)*vp;
-        *qp = fdiv(fadd(fmul(vf, *qp), fsub(1.f, value)), fadd(vf, 1.f));               // :319
-        *vp = (uint16_t)(*vp + 1);                                                       // :320
-        uint16_t* nv = reinterpret_cast<uint16_t*>(nrec + Lay::OFF_AUX + 6);            // NodeAux::nvis
-        *nv = (uint16_t)(*nv + 1);
-      }
-      const NodeHdr nh = *reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR);
-      move = nh.action; nindex = nh.parent;                                              // :322-323
-      value = fsub(1.f, value);                                                          // :324
+      *qp = qnew;
+      *vp = (uint16_t)(vold + 1);                                                        // :320
+      *nv = (uint16_t)(nvold + 1);
     }
   }
 }
 
 template <class G, bool INJECT>
-__global__ void __launch_bounds__(256) expand_backup_kernel(SearchParams P, int L, int training, int last_rollout,
+__global__ void __launch_bounds__(Layout<G>::SB) expand_backup_kernel(SearchParams P, int L, int training, int last_rollout,
                                                             const float* __restrict__ prior_in, const float* __restrict__ value_in, float cpuct) {
   constexpr int W = Layout<G>::W;
+  __shared__ __align__(16) float s_sel[(Layout<G>::SB / W) * SelScratch<G>::FLOATS];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   if (g >= L) return;
-  expand_backup_game<G, INJECT>(P, g, threadIdx.x & (W - 1), group_mask<W>(), training, last_rollout, prior_in, value_in, cpuct);
+  expand_backup_game<G, INJECT>(P, g, threadIdx.x & (W - 1), group_mask<W>(), training, last_rollout, prior_in, value_in, cpuct,
+                                s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 
 // One launch per rollout for the search side: expand + backUp of rollout k-1 (its network output is ready) followed at once by the
 // descent of rollout k.  The group that just walked a game's path back up re-descends through the same, still cached, records.
 template <class G>
-__global__ void __launch_bounds__(256, AG_MINBLOCKS) step_kernel(SearchParams P, int L, int rollout, int last_rollout, int training, float cpuct, u64 seed,
+__global__ void __launch_bounds__(Layout<G>::SB, Layout<G>::SB_MIN) step_kernel(SearchParams P, int L, int rollout, int last_rollout, int training, float cpuct, u64 seed,
                                                    u32 ply) {
   constexpr int W = Layout<G>::W;
-  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
+  __shared__ __align__(16) float s_sel[(Layout<G>::SB / W) * SelScratch<G>::FLOATS];
   const int g = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   if (g >= L) return;
   const int l = threadIdx.x & (W - 1);
   const unsigned gm = group_mask<W>();
-  expand_backup_game<G, false>(P, g, l, gm, training, 0, nullptr, nullptr, cpuct);
+  expand_backup_game<G, false>(P, g, l, gm, training, 0, nullptr, nullptr, cpuct, s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
   __syncwarp(gm);                                      // the group's global writes (q, visits, prior, flags) are ordered before its reads
   select_game<G>(P, g, l, gm, L, rollout, last_rollout, cpuct, nullptr, seed, ply, s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 
 // ---- the same three launches, addressed through a SegParams record (graph replay, one stream per slice) ----
 template <class G>
-__global__ void __launch_bounds__(256, AG_MINBLOCKS) select_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
+__global__ void __launch_bounds__(Layout<G>::SB, Layout<G>::SB_MIN) select_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
   constexpr int W = Layout<G>::W;
-  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
+  __shared__ __align__(16) float s_sel[(Layout<G>::SB / W) * SelScratch<G>::FLOATS];
   const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   const SegParams S = *sp;
   if (gl >= S.len) return;
@@ -1217,25 +1238,27 @@ __global__ void __launch_bounds__(256, AG_MINBLOCKS) select_seg_kernel(SearchPar
                  s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 template <class G>
-__global__ void __launch_bounds__(256, AG_MINBLOCKS) step_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
+__global__ void __launch_bounds__(Layout<G>::SB, Layout<G>::SB_MIN) step_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int rollout, int last_rollout) {
   constexpr int W = Layout<G>::W;
-  __shared__ __align__(16) float s_sel[(256 / W) * SelScratch<G>::FLOATS];
+  __shared__ __align__(16) float s_sel[(Layout<G>::SB / W) * SelScratch<G>::FLOATS];
   const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   const SegParams S = *sp;
   if (gl >= S.len) return;
   const int g = S.off + gl, l = threadIdx.x & (W - 1);
   const unsigned gm = group_mask<W>();
-  expand_backup_game<G, false>(P, g, l, gm, S.training, 0, nullptr, nullptr, S.cpuct);
+  expand_backup_game<G, false>(P, g, l, gm, S.training, 0, nullptr, nullptr, S.cpuct, s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
   __syncwarp(gm);
   select_game<G>(P, g, l, gm, 0, rollout, last_rollout, S.cpuct, nullptr, S.seed, S.ply, s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 template <class G>
-__global__ void __launch_bounds__(256) expand_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int last_rollout) {
+__global__ void __launch_bounds__(Layout<G>::SB) expand_seg_kernel(SearchParams P, const SegParams* __restrict__ sp, int last_rollout) {
   constexpr int W = Layout<G>::W;
+  __shared__ __align__(16) float s_sel[(Layout<G>::SB / W) * SelScratch<G>::FLOATS];
   const int gl = (blockIdx.x * blockDim.x + threadIdx.x) / W;
   const SegParams S = *sp;
   if (gl >= S.len) return;
-  expand_backup_game<G, false>(P, S.off + gl, threadIdx.x & (W - 1), group_mask<W>(), S.training, last_rollout, nullptr, nullptr, S.cpuct);
+  expand_backup_game<G, false>(P, S.off + gl, threadIdx.x & (W - 1), group_mask<W>(), S.training, last_rollout, nullptr, nullptr, S.cpuct,
+                               s_sel + (threadIdx.x / W) * SelScratch<G>::FLOATS);
 }
 
 // ------------------------------------------------------------------------------------------------
