@@ -155,7 +155,7 @@ struct EngineT : EngineBase {
   // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
   static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;   // and width 128, checked at run time
   bool use_fused = false;
-  int num_sms = 148, fused_min_gpc = 8;
+  int num_sms = 148, fused_min_gpc = 8, fused_pair_min = 1 << 30;   // (paired configuration: off unless AGPU_FUSED_PAIR_MIN)
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -270,6 +270,11 @@ struct EngineT : EngineBase {
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
+        if (const char* e = getenv("AGPU_FUSED_PAIR_MIN")) fused_pair_min = atoi(e);
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 256>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 256>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         cudaDeviceProp prop;
         AG_CK(cudaGetDeviceProperties(&prop, cfg.device));
         num_sms = prop.multiProcessorCount;
@@ -292,10 +297,17 @@ struct EngineT : EngineBase {
       gpc = (gpc + 7) / 8 * 8;
       if (gpc < fused_min_gpc) gpc = fused_min_gpc;
       if (gpc > 256) gpc = 256;
+      // above fused_pair_min games per SM: two CTAs of half as many games per SM (the paired configuration)
+      const bool paired = gpc >= fused_pair_min && (gpc / 2 + 7) / 8 * 8 <= fused::FCfg<G, 1, 256>::GAMES;
+      if (paired) gpc = std::max(8, (gpc / 2 + 7) / 8 * 8);
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (gpc <= 128) {
+        if (paired) {
+          typedef fused::FCfg<G, 1, 256> CP;
+          if (fmt == 0) fused::ply_kernel<G, 0, 1, 256><<<grid, CP::THREADS, CP::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1, 256><<<grid, CP::THREADS, CP::SMEM, stream>>>(P, T, S, visits, gpc);
+        } else if (gpc <= 128) {
           // the tail of a generation: at most one tile per CTA -> the small-batch kernel (swapped orientation up to 64 games, node cache)
           if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);

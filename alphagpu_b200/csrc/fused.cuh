@@ -36,21 +36,27 @@ using namespace tc;
 // NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
-template <class G, int NT> struct FCfg {
-  static constexpr int THREADS = 512;
-  static constexpr int WPT = 16 / NT;                                  // warps per tile
+// TH = 256 (with NT = 1): the PAIRED configuration — one tile, 8 warps, half the shared memory and a quarter of the tensor memory, so that
+// TWO CTAs of <= 128 games share an SM and drift out of phase: one's network chain (a latency chain that leaves most issue slots and
+// the load/store path idle) runs under the other's search phases.
+template <class G, int NT, int TH = 512> struct FCfg {
+  static constexpr int THREADS = TH;
+  static constexpr bool PAIRED = (NT == 1 && TH == 256);
+  static constexpr int WPT = (TH / 32) / NT;                           // warps per tile
   static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
-  static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
+  static constexpr int GAMES = PAIRED ? 120 : NT * TC_TILE_M;          // games per CTA (capacity; paired: what fits twice in an SM's shared memory)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * ITEMS_PER_GAME + 2 + 2 * PATH_SMEM_DEPTH;
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
-  static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
+  static constexpr int TREE_BYTES = (NT == 1 && !PAIRED) ? 64 * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
-  // tensor memory: NT x 128 accumulator columns + NT x 128 columns of fp32 residual stream; the small-batch kernel takes all 512 columns
-  // and, in the swapped orientation, keeps the trunk weights — the A operand there — resident in columns 64..511 (TW_COL0 + 64 per layer)
-  static constexpr int TMEM_COLS = 512;
+  // tensor memory: 128 accumulator columns per tile (the fp32 residual stream is in registers); the small-batch kernel takes all 512
+  // columns and, in the swapped orientation, keeps the trunk weights — the A operand there — resident in columns 64..511
+  // (TW_COL0 + 64 per layer)
+  static constexpr int TMEM_COLS = PAIRED ? 128 : 512;
   static constexpr int TW_COL0 = 64, TW_MAX_LAYERS = 7;
-  static_assert(SMEM <= 227 * 1024, "shared memory per CTA");
+  static_assert(SMEM <= (PAIRED ? (228 * 1024 - 2 * 1024) / 2 : 227 * 1024), "shared memory per CTA (1 KB per resident CTA is reserved)");
+  static_assert(TH == 512 || PAIRED, "512 threads, or 256 for the paired one-tile configuration");
 };
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -74,16 +80,14 @@ AG_D void tmem_ldn(uint32_t taddr, uint32_t (&v)[16]) { tmem_ld16(taddr, v); }
 // residual stream stays in its registers (sres); it applies relu / the residual and scatters the 16-bit operand of the next layer into
 // the ordinary games x features, K-major, 128B-swizzled tile (so the head layer and the encoder need no second layout).
 template <int FMT, int NC>
-AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, int l, unsigned char* At, uint32_t (&sres)[16]) {
+AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, unsigned char* At, uint32_t (&sres)[16]) {
   uint32_t va[NC];
   const uint32_t taddr = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs * NC);
   tmem_ldn(tmem_acc + taddr, va);
   tmem_ld_wait();
 #pragma unroll
   for (int e = 0; e < NC; e++) {
-    const float ra = fmaxf(__uint_as_float(va[e]), 0.f);
-    const float hv = (l == 0) ? ra : __uint_as_float(sres[e]) + ra;
-    sres[e] = __float_as_uint(hv);
+    sres[e] = __float_as_uint(__uint_as_float(sres[e]) + fmaxf(__uint_as_float(va[e]), 0.f));   // (sres starts at zero before the base layer)
   }
   const int f = 32 * wq + lane;
   unsigned char* base = At + (f >> 6) * TC_KTILE_BYTES_A + (f & 7) * 2;
@@ -96,43 +100,37 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, int l, u
 }
 
 // Epilogue of a trunk layer in the ordinary orientation: row r = 32*wq + lane of the tile, NSL consecutive 32-column slices from cs0.
-// b = relu(acc) (base layer) or b + relu(acc); fp32 residual in TMEM; next A operand = fp16/bf16(b).
+// b = relu(acc) (base layer) or b + relu(acc); the fp32 residual stream stays in this thread's registers for the whole chain (res: it
+// owns the same row and columns in every layer; they are dead registers of the search phases); next A operand = fp16/bf16(b).
 // The tensor-memory loads of a 16-column chunk are issued before the previous chunk is processed (tcgen05.wait::ld waits for ALL
 // outstanding loads, so without this the load latency is exposed once per chunk: 4 or 8 times per layer).
 template <int FMT, int NSL>
-AG_D void epilogue_ordinary(uint32_t tmem_acc, uint32_t tmem_res, int wq, int cs0, int lane, int l, bool keep, unsigned char* At) {
+AG_D void epilogue_ordinary(uint32_t tmem_acc, int wq, int cs0, int lane, unsigned char* At, uint32_t (&res)[32 * NSL]) {
   const int r = wq * 32 + lane;
   const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs0 * 32);
   constexpr int NCH = 2 * NSL;                                          // 16-column chunks
-  uint32_t va[2][16], vh[2][16];
+  uint32_t va[2][16];
   tmem_ld16(tmem_acc + lane_sel, va[0]);
-  if (l > 0) tmem_ld16(tmem_res + lane_sel, vh[0]);
 #pragma unroll
   for (int i = 0; i < NCH; i++) {
     const int b = i & 1;
     tmem_ld_wait();                                                     // chunk i has arrived
-    if (i + 1 < NCH) {                                                  // chunk i + 1 in flight while chunk i is processed
-      tmem_ld16(tmem_acc + lane_sel + 16 * (i + 1), va[b ^ 1]);
-      if (l > 0) tmem_ld16(tmem_res + lane_sel + 16 * (i + 1), vh[b ^ 1]);
-    }
+    if (i + 1 < NCH) tmem_ld16(tmem_acc + lane_sel + 16 * (i + 1), va[b ^ 1]);   // chunk i + 1 in flight while chunk i is processed
 #pragma unroll
     for (int e = 0; e < 16; e++) {
-      const float ra = fmaxf(__uint_as_float(va[b][e]), 0.f);
-      const float hv = (l == 0) ? ra : __uint_as_float(vh[b][e]) + ra;
-      vh[b][e] = __float_as_uint(hv);
+      // (the caller zeroes res before the base layer: 0 + relu(acc) is relu(acc), and no select per element is spent on l == 0)
+      res[16 * i + e] = __float_as_uint(__uint_as_float(res[16 * i + e]) + fmaxf(__uint_as_float(va[b][e]), 0.f));
     }
-    if (keep) tmem_st16(tmem_res + lane_sel + 16 * i, vh[b]);
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
       const int c = 4 * cs0 + 2 * i + c2;
-      const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 0]), __uint_as_float(vh[b][8 * c2 + 1])),
-                                  pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 2]), __uint_as_float(vh[b][8 * c2 + 3])),
-                                  pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 4]), __uint_as_float(vh[b][8 * c2 + 5])),
-                                  pack2<FMT>(__uint_as_float(vh[b][8 * c2 + 6]), __uint_as_float(vh[b][8 * c2 + 7])));
+      const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 0]), __uint_as_float(res[16 * i + 8 * c2 + 1])),
+                                  pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 2]), __uint_as_float(res[16 * i + 8 * c2 + 3])),
+                                  pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 4]), __uint_as_float(res[16 * i + 8 * c2 + 5])),
+                                  pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 6]), __uint_as_float(res[16 * i + 8 * c2 + 7])));
       *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
     }
   }
-  tmem_st_wait();
 }
 
 // development trace: BAR.SYNC.DEFER_BLOCKING does not block at issue but at the next consumer, so a clock read placed right behind a
@@ -143,12 +141,12 @@ AG_D long long clock_after_barrier(const void* smem_word) {
   return clock64() + (long long)(d & 0u);
 }
 
-template <class G, int FMT, int NT>
-__global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+template <class G, int FMT, int NT, int TH = 512>
+__global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   typedef Layout<G> Lay;
-  typedef FCfg<G, NT> C;
+  typedef FCfg<G, NT, TH> C;
   typedef typename G::State State;
-  constexpr bool SMALL = NT == 1;                                      // the small-batch kernel: swapped orientation, node cache
+  constexpr bool SMALL = NT == 1 && !C::PAIRED;                        // the small-batch kernel: swapped orientation, node cache
   constexpr int W = Lay::W;
   constexpr int STAGES = C::STAGES;
   static_assert(Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= TC_N, "fused ply kernel: small boards only");
@@ -241,7 +239,6 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   const int r = wq * 32 + lane;
   unsigned char* At = sA + t * TC_A_BYTES;
   const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
-  const uint32_t tmem_res = tmem_base + (uint32_t)(NT * TC_N + t * TC_N);
   // The MMA-issuing warp of a tile takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived
   // from values the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent
   // `lane == 0` branch each MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
@@ -414,7 +411,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
-    const bool obs = AG_TRACE >= 2 && dbg_on && threadIdx.x == 256;    // development trace: a non-issuing warp's view of the network phase
+    const bool obs = AG_TRACE >= 2 && dbg_on && threadIdx.x == TH / 2;    // development trace: a non-issuing warp's view of the network phase
     long long ob0 = 0;
     if (obs) ob0 = clock_after_barrier(s_next);
     {
@@ -448,6 +445,11 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
       named_bar_sync(NT == 1 ? 2 : 2 + t, 32 * WPT);   // (a compile-time barrier id where there is one tile)
       if (obs) { const long long c = clock_after_barrier(s_next); T.dbg[blockIdx.x * 128 + 64] += c - ob0; ob0 = c; }
       uint32_t sres[16];                                               // this thread's residual values (swapped orientation)
+#pragma unroll
+      for (int e = 0; e < 16; e++) sres[e] = 0u;
+      uint32_t rres[32 * CPW];                                         // ... and in the ordinary orientation (starts at zero)
+#pragma unroll
+      for (int e = 0; e < 32 * CPW; e++) rres[e] = 0u;
       for (int l = 0; l < nlayers; l++) {
         const int wll = wl + l;
         const int s = wll % STAGES;
@@ -477,10 +479,10 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
         if (!is_head) {
           if (SMALL && swapped) {
-            if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, l, At, sres);
-            else epilogue_swapped<FMT, 16>(tmem_acc, wq, csb, lane, l, At, sres);
+            if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, At, sres);
+            else epilogue_swapped<FMT, 16>(tmem_acc, wq, csb, lane, At, sres);
           } else {
-            epilogue_ordinary<FMT, CPW>(tmem_acc, tmem_res, wq, csb, lane, l, l + 2 < nlayers, At);   // the last trunk layer's residual is not read again
+            epilogue_ordinary<FMT, CPW>(tmem_acc, wq, csb, lane, At, rres);
           }
           tc_fence_before();
           fence_proxy_async();
