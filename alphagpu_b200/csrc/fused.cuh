@@ -33,6 +33,7 @@ using namespace tc;
 #define AG_TRACE 0
 #endif
 
+
 // NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
@@ -105,10 +106,11 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, unsigned
 // The tensor-memory loads of a 16-column chunk are issued before the previous chunk is processed (tcgen05.wait::ld waits for ALL
 // outstanding loads, so without this the load latency is exposed once per chunk: 4 or 8 times per layer).
 template <int FMT, int NSL>
-AG_D void epilogue_ordinary(uint32_t tmem_acc, int wq, int cs0, int lane, unsigned char* At, uint32_t (&res)[32 * NSL]) {
+AG_D void epilogue_ordinary(uint32_t tmem_acc, int wq, int cs0, int lane, unsigned char* At, f32x2 (&res)[16 * NSL]) {
   const int r = wq * 32 + lane;
   const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs0 * 32);
   constexpr int NCH = 2 * NSL;                                          // 16-column chunks
+  const f32x2 half2 = pack2f(0.5f, 0.5f);
   uint32_t va[2][16];
   tmem_ld16(tmem_acc + lane_sel, va[0]);
 #pragma unroll
@@ -116,19 +118,25 @@ AG_D void epilogue_ordinary(uint32_t tmem_acc, int wq, int cs0, int lane, unsign
     const int b = i & 1;
     tmem_ld_wait();                                                     // chunk i has arrived
     if (i + 1 < NCH) tmem_ld16(tmem_acc + lane_sel + 16 * (i + 1), va[b ^ 1]);   // chunk i + 1 in flight while chunk i is processed
+    // res += relu(acc), two columns per FFMA2: a + |a| is 2 relu(a) exactly, and fma(2 relu(a), 0.5, res) rounds once, like the add — one
+    // FADD per column and one packed FFMA per pair on the FMA pipe instead of an FMNMX (half-rate ALU pipe) and an FADD per column.
+    // (The caller zeroes res before the base layer: no select per element is spent on l == 0.)
 #pragma unroll
-    for (int e = 0; e < 16; e++) {
-      // (the caller zeroes res before the base layer: 0 + relu(acc) is relu(acc), and no select per element is spent on l == 0)
-      res[16 * i + e] = __float_as_uint(__uint_as_float(res[16 * i + e]) + fmaxf(__uint_as_float(va[b][e]), 0.f));
+    for (int e = 0; e < 8; e++) {
+      const float a0 = __uint_as_float(va[b][2 * e]), a1 = __uint_as_float(va[b][2 * e + 1]);
+      res[8 * i + e] = fma2(pack2f(__fadd_rn(a0, fabsf(a0)), __fadd_rn(a1, fabsf(a1))), half2, res[8 * i + e]);
     }
 #pragma unroll
     for (int c2 = 0; c2 < 2; c2++) {
       const int c = 4 * cs0 + 2 * i + c2;
-      const uint4 pk = make_uint4(pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 0]), __uint_as_float(res[16 * i + 8 * c2 + 1])),
-                                  pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 2]), __uint_as_float(res[16 * i + 8 * c2 + 3])),
-                                  pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 4]), __uint_as_float(res[16 * i + 8 * c2 + 5])),
-                                  pack2<FMT>(__uint_as_float(res[16 * i + 8 * c2 + 6]), __uint_as_float(res[16 * i + 8 * c2 + 7])));
-      *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = pk;
+      uint32_t pk[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        float lo, hi;
+        unpack2f(res[8 * i + 4 * c2 + e], lo, hi);
+        pk[e] = pack2<FMT>(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
     }
   }
 }
@@ -197,7 +205,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) ply_kernel(SearchParams
   // the search phase reads the outputs in between
   SH.out = reinterpret_cast<float*>(sA);
   SH.out_tile_stride = TC_A_BYTES / 4;
-  static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_A_BYTES, "the network's outputs live in the idle A tile");
+  static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_KTILE_BYTES_A, "the network's outputs live in the first K tile of the idle A tile");
   // node cache (small-batch kernel): the first nc_nodes nodes of each of this CTA's games; the fewer games, the deeper the cache
   SH.nc_base = reinterpret_cast<unsigned char*>(bars) + C::WORK;
   SH.nc_nodes = SMALL ? min(P.R, C::TREE_BYTES / (CacheSlot<Lay::APAD>::BYTES * count)) : 0;
@@ -428,13 +436,18 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) ply_kernel(SearchParams
 #pragma unroll
       for (int j = 0; j < CPW; j++) {
         const int cs = csb + j;
+        // (warp-uniform) columns beyond the input: zero weights in the base layer's image, zeros written by the first rollout, finite
+        // activations afterwards — nothing to encode.  Columns 0..63 are always rewritten: the network's outputs (fp32, any bit pattern)
+        // were parked in the first K tile.  (Skipping the K-steps in the MMA sequence instead costs far more than it saves: a branch
+        // between two tcgen05.mma stalls the issue, +2.8 ms per generation on B200.)
+        if (k > 0 && 32 * cs >= max(16 * T.k0_steps, 64)) continue;
         const uint32_t bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const uint32_t byte = (bits >> (8 * i)) & 0xFFu;
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
+          for (int e = 0; e < 4; e++) w[e] = bits2_to_operands(byte >> (2 * e), one);
           const int c = 4 * cs + i;                                    // chunk of 8 operands in the row, 0..15
           *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
@@ -447,9 +460,9 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) ply_kernel(SearchParams
       uint32_t sres[16];                                               // this thread's residual values (swapped orientation)
 #pragma unroll
       for (int e = 0; e < 16; e++) sres[e] = 0u;
-      uint32_t rres[32 * CPW];                                         // ... and in the ordinary orientation (starts at zero)
+      f32x2 rres[16 * CPW];                                            // ... and in the ordinary orientation, as pairs (starts at zero)
 #pragma unroll
-      for (int e = 0; e < 32 * CPW; e++) rres[e] = 0u;
+      for (int e = 0; e < 16 * CPW; e++) rres[e] = 0ull;
       for (int l = 0; l < nlayers; l++) {
         const int wll = wl + l;
         const int s = wll % STAGES;

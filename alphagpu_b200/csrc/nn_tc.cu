@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tc_mlp128_kernel(TcArgs T, NNIn
           const uint32_t byte = (uint32_t)(xh >> (8 * cl)) & 0xFFu;
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
+          for (int e = 0; e < 4; e++) w[e] = bits2_to_operands(byte >> (2 * e), one);
           *reinterpret_cast<uint4*>(At + ch * TC_KTILE_BYTES_A + r * 128 + ((cl ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       } else {

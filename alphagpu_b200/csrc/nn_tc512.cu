@@ -187,7 +187,7 @@ __global__ void __maxnreg__(W5_MAXREG) tc_mlp512_kernel(Tc512Args T, NNInput I, 
           const uint32_t byte = (uint32_t)(bits >> (8 * i)) & 0xFFu;
           uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) w[e] = ((byte >> (2 * e)) & 1u) * one | (((byte >> (2 * e + 1)) & 1u) * one) << 16;
+          for (int e = 0; e < 4; e++) w[e] = bits2_to_operands(byte >> (2 * e), one);
           *reinterpret_cast<uint4*>(chunk_ptr(8 * cs + i)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }

@@ -129,6 +129,10 @@ template <int FMT> AG_D uint32_t pack2(float lo, float hi) {
   return d;
 }
 
+// bits 0 and 1 of t (t < 2^16) -> one packed pair of MMA operands {bit 0 ? 1.0 : 0, bit 1 ? 1.0 : 0}; `one` = the 16-bit pattern of 1.0.
+// t * 0x8001 puts bit 0 at position 0 and bit 1 at position 16; the mask keeps those two; the product with `one` cannot carry.
+AG_D uint32_t bits2_to_operands(uint32_t t, uint32_t one) { return ((t * 0x8001u) & 0x00010001u) * one; }
+
 struct TcArgs {
   const unsigned char* img;   // layer images, back to back
   const float* bias;          // [NH] head biases
