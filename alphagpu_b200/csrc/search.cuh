@@ -21,7 +21,10 @@
 
 namespace ag {
 
-enum : uint8_t { F_EXPANDED = 1, F_TERMINAL = 2 };
+// F_PRIOR_BOX (FAST layouts, set by expand): every prior of the node is +0 or >= 2^-50, which — with λ in [2^-10, 2^10] — puts every
+// numerator of the α-solve (λ·prior, λ·Σ prior) inside the operand box of fdiv_fast without looking at them again
+enum : uint8_t { F_EXPANDED = 1, F_TERMINAL = 2, F_PRIOR_BOX = 4 };
+constexpr float PRIOR_BOX_LO = 8.881784197001252e-16f;   // 2^-50
 
 struct alignas(8) NodeHdr {
   uint8_t parent;   // 1-based node id, 0 = root has none            (vnodes.parent)
@@ -270,7 +273,7 @@ template <int AP> AG_D float sel_reg(const float (&v)[AP], const int idx) {
 
 template <int A, int AP>
 AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis)[AP], const int (&ch)[AP], const int (&ord)[AP],
-                     const int nchild, const float cpuct, float (&pol)[AP], long long* tr = nullptr) {
+                     const int nchild, const float cpuct, const bool prior_box, float (&pol)[AP], long long* tr = nullptr) {
   int nv = 0, acount = 0;
   float rem = 0.f;
 #pragma unroll
@@ -301,19 +304,22 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
   }
   // Fast-division plan (common.cuh: fdiv_fast): every numerator below is loop-invariant and non-negative, every denominator positive.
   // The derivative is summed with all signs flipped, G = rem/α² + Σ tops/bot² = -gs: rounding is sign-symmetric, so -G is bit for bit the
-  // reference's gs, and α - err/gs = α + err/G.  Denominators are box-checked through their running min / max.
+  // reference's gs, and α - err/gs = α + err/G.
+  // Operand checks in O(1): the numerators are λ·prior and λ·Σ prior — in the box when the node's priors are (F_PRIOR_BOX, decided once
+  // by expand) and λ is in [2^-10, 2^10].  The denominators of an iteration are α and α - q_k: rounding is monotone, so the smallest and
+  // the largest of them are α - max(0, q) and α - min(0, q), with the q range taken once per solve (an action without a child has q = 0).
   constexpr float SQ_LO = 9.313225746154785e-10f, SQ_HI = 1073741824.0f;             // 2^-30, 2^30: the squares stay inside the box
-  bool num_ok = fdiv_box_num(rem);
+  float qmin = 0.f, qmax = 0.f;
 #pragma unroll
-  for (int k = 0; k < A; k++) num_ok = num_ok && fdiv_box_num(tops[k]);
+  for (int a = 0; a < A; a++) { qmin = fminf(qmin, q[a]); qmax = fmaxf(qmax, q[a]); }
+  const bool num_ok = prior_box && lambda >= 0.0009765625f && lambda <= 1024.0f;
   float err = __int_as_float(0x7f800000);
   const long long trs = tr ? clock64() + (__float_as_int(alpha) & 0) + (__float_as_int(tops[0]) & 0) + (__float_as_int(qs[A - 1]) & 0): 0;
   for (int it = 0; it < 100; it++) {                                                 // :141-162
     float bot[AP];
-    float bmin = alpha, bmax = alpha;
 #pragma unroll
-    for (int k = 0; k < A; k++) { bot[k] = fsub(alpha, qs[k]); bmin = fminf(bmin, bot[k]); bmax = fmaxf(bmax, bot[k]); }
-    const bool fast = num_ok && bmin >= SQ_LO && bmax <= SQ_HI;                      // (a NaN denominator fails the comparison chain below)
+    for (int k = 0; k < A; k++) bot[k] = fsub(alpha, qs[k]);
+    const bool fast = num_ok && fsub(alpha, qmax) >= SQ_LO && fsub(alpha, qmin) <= SQ_HI;   // (a NaN fails the comparisons)
     float S;
     if (fast) {
       // all quotients first — independent, branch-free, staged so that they overlap in the pipeline — then the adds in reference order
@@ -342,7 +348,7 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
       float G = nq[0];
 #pragma unroll
       for (int k = 0; k < A; k++) if (k < nchild) G = fadd(G, nq[k + 1]);
-      alpha = fadd(alpha, fdiv(newerr, G));
+      alpha = fadd(alpha, (fdiv_box_num_bits(newerr) && fdiv_box_den_bits(G)) ? fdiv_fast(newerr, G) : fdiv(newerr, G));
     } else {
       float gs = fdiv(-rem, fmul(alpha, alpha));
 #pragma unroll
@@ -355,10 +361,9 @@ AG_D void solve_node(const float (&p)[AP], const float (&q)[AP], const int (&vis
   {
     // π̄_a = λ p_a / (α - q_a) (:165-169)
     float num[A], den[A];
-    bool ok = true;
 #pragma unroll
-    for (int a = 0; a < A; a++) { num[a] = top[a]; den[a] = fsub(alpha, q[a]); ok = ok && fdiv_box_den(den[a]) && fdiv_box_num(num[a]); }
-    if (ok) {
+    for (int a = 0; a < A; a++) { num[a] = top[a]; den[a] = fsub(alpha, q[a]); }
+    if (num_ok && fsub(alpha, qmax) >= FDIV_BOX_LO && fsub(alpha, qmin) <= FDIV_BOX_HI) {
       float nq[A];
       fdiv_fast_n<A>(num, den, nq);
 #pragma unroll
@@ -746,7 +751,14 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
       if (Lay::FAST) *reinterpret_cast<float*>(rec + Lay::OFF_POLICY + 4 * a) = pr;      // policy[:,leaf] = prior[:,leaf]  (:297-299)
       if (leaf == 0 && last_rollout && a < A) P.policy_final[(size_t)g * A + a] = pr;    // R == 1: policy[:,1] is the prior itself
     }
-    if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
+    uint8_t nflags = (uint8_t)(h.flags | F_EXPANDED);
+    if constexpr (Lay::FAST) {
+      bool pbox = true;
+#pragma unroll
+      for (int j = 0; j < APL; j++) pbox = pbox && (__float_as_uint(prv[j]) == 0u || prv[j] >= PRIOR_BOX_LO);
+      if (__all_sync(gm, pbox)) nflags |= F_PRIOR_BOX;
+    }
+    if (l == 0) reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = nflags;         // :256
     if constexpr (!Lay::FAST) {
       // NodeAux of the freshly expanded node: no child yet, so prior_rem is the ascending sum of the whole prior; #{prior > 0}; no visits
       int pos = 0;
@@ -820,7 +832,9 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
         }
-        const int nchild = reinterpret_cast<const NodeHdr*>(nrec + Lay::OFF_HDR)->nchild;
+        const uint32_t hw = *reinterpret_cast<const uint32_t*>(nrec + Lay::OFF_HDR);   // parent | action | nchild | flags
+        const int nchild = (int)((hw >> 16) & 0xFFu);
+        const bool prior_box = ((hw >> 24) & F_PRIOR_BOX) != 0;
         // running mean of the child's value from this node's point of view (:319-320)
         float qold = 0.f; int vold = 0;
 #pragma unroll
@@ -843,7 +857,7 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
         long long tr1 = 0;
         if (tr) { tr1 = clock64() + (__float_as_int(qnew) & 0); tr[0] += tr1 - tr0; }
         if (!last_rollout) {
-          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, pol, tr);
+          solve_node<A, AP>(p, q, vis, ch, ord, nchild, cpuct, prior_box, pol, tr);
           if (tr) { tr[1] += clock64() + (__float_as_int(pol[0]) & 0) - tr1; tr[2] += 1; }
 #pragma unroll
           for (int c = 0; c < AP / 4; c++)
@@ -1122,13 +1136,17 @@ AG_D void expand_game1(const SearchParams& P, const int g, const int gl, const R
 #pragma unroll
       for (int a = 0; a < A; a++) P.policy_final[(size_t)g * A + a] = pr[a];
     }
-    reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = (uint8_t)(h.flags | F_EXPANDED);   // :256
+    bool pbox = true;
+#pragma unroll
+    for (int a = 0; a < A; a++) pbox = pbox && (__float_as_uint(pr[a]) == 0u || pr[a] >= PRIOR_BOX_LO);
+    const uint8_t nflags = (uint8_t)(h.flags | F_EXPANDED | (pbox ? F_PRIOR_BOX : 0));
+    reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->flags = nflags;                     // :256
     if (CACHE) {
       if (unsigned char* sl = node_cache_slot<G, CACHE>(SH, gl, leaf)) {                 // write-through: π̄ = prior, expanded flag
 #pragma unroll
         for (int c = 0; c < AP / 4; c++)
           *reinterpret_cast<float4*>(sl + CS::OFF_POLICY + 16 * c) = make_float4(pr[4 * c], pr[4 * c + 1], pr[4 * c + 2], pr[4 * c + 3]);
-        sl[3] = (uint8_t)(h.flags | F_EXPANDED);                                         // NodeHdr::flags
+        sl[3] = nflags;                                                                  // NodeHdr::flags
       }
     }
   }
