@@ -111,11 +111,12 @@ struct EngineT : EngineBase {
   static constexpr int A = G::A;
 
   cudaStream_t stream = nullptr;
-  // AGPU_STREAM_SAMPLES=1 (development switch, NOT YET RUN ON A GPU): the rows a ply appends to the sample arrays (state, policy, player,
-  // game, ply — final when pushed) are copied to the caller's buffers on a second stream while the next ply searches; only value and
-  // fstate, which need the game's end, are copied after the loop (26 of 96 MB at the bench size)
+  // Sample streaming: the rows a ply appends to the sample arrays (state, policy, player, game, ply — final when pushed) are copied to the
+  // caller's buffers on a second stream while the next ply searches; only value and fstate, which need the game's end, are copied after
+  // the loop (26 of 96 MB at the bench size; B200: 66.1 -> 65.2 ms per generation end to end).  Used when the caller's arrays are
+  // page-locked (a pageable destination would make every copy a blocking one); AGPU_STREAM_SAMPLES=0 switches it off.
   cudaStream_t copy_stream = nullptr;
-  bool stream_samples = false;
+  bool stream_samples = true;
   int64_t L_cap = 0;
   int R = 0;
   int64_t L_live = 0;
@@ -155,7 +156,7 @@ struct EngineT : EngineBase {
   // fused per-ply kernel (fused.cuh): available for small boards with the tensor-core chain
   static constexpr bool FUSED_OK = Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= tc::TC_N;   // and width 128, checked at run time
   bool use_fused = false;
-  int num_sms = 148, fused_min_gpc = 8, fused_pair_min = 1 << 30;   // (paired configuration: off unless AGPU_FUSED_PAIR_MIN)
+  int num_sms = 148, fused_min_gpc = 8;
   // profiling
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int cls; };
@@ -232,7 +233,7 @@ struct EngineT : EngineBase {
     AG_CK(cudaSetDevice(cfg.device));
     AG_CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (const char* e = getenv("AGPU_STREAM_SAMPLES")) stream_samples = atoi(e) != 0;
-    if (stream_samples) AG_CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
+    AG_CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     L_cap = cfg.max_games; R = cfg.rollouts;
     AG_CK(tree.ensure((size_t)L_cap * R * Lay::REC));
     AG_CK(nnodes.ensure(L_cap)); AG_CK(leaf.ensure(L_cap)); AG_CK(uid.ensure(L_cap)); AG_CK(uid_b.ensure(L_cap));
@@ -270,11 +271,6 @@ struct EngineT : EngineBase {
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
-        if (const char* e = getenv("AGPU_FUSED_PAIR_MIN")) fused_pair_min = atoi(e);
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 256>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 256>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, 256>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         cudaDeviceProp prop;
         AG_CK(cudaGetDeviceProperties(&prop, cfg.device));
         num_sms = prop.multiProcessorCount;
@@ -282,6 +278,12 @@ struct EngineT : EngineBase {
     }
     AG_CK(cudaStreamSynchronize(stream));
     return AGPU_OK;
+  }
+
+  static bool host_pinned(const void* p) {
+    cudaPointerAttributes a;
+    if (p == nullptr || cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
   }
 
   // one launch for the whole rollout loop of a ply (fused.cuh)
@@ -297,17 +299,10 @@ struct EngineT : EngineBase {
       gpc = (gpc + 7) / 8 * 8;
       if (gpc < fused_min_gpc) gpc = fused_min_gpc;
       if (gpc > 256) gpc = 256;
-      // above fused_pair_min games per SM: two CTAs of half as many games per SM (the paired configuration)
-      const bool paired = gpc >= fused_pair_min && (gpc / 2 + 7) / 8 * 8 <= fused::FCfg<G, 1, 256>::GAMES;
-      if (paired) gpc = std::max(8, (gpc / 2 + 7) / 8 * 8);
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (paired) {
-          typedef fused::FCfg<G, 1, 256> CP;
-          if (fmt == 0) fused::ply_kernel<G, 0, 1, 256><<<grid, CP::THREADS, CP::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 1, 256><<<grid, CP::THREADS, CP::SMEM, stream>>>(P, T, S, visits, gpc);
-        } else if (gpc <= 128) {
+        if (gpc <= 128) {
           // the tail of a generation: at most one tile per CTA -> the small-batch kernel (swapped orientation up to 64 games, node cache)
           if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
           else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
@@ -790,7 +785,8 @@ struct EngineT : EngineBase {
     double t_prev = 0;
     auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
     if (trace_plies) t_prev = now_ms();
-    const bool streaming = stream_samples && !duel && samples != nullptr && samples->capacity > 0;
+    const bool streaming = stream_samples && !duel && samples != nullptr && samples->capacity > 0 && host_pinned(samples->state) &&
+                           host_pinned(samples->policy) && host_pinned(samples->player);
     if (streaming) AG_REQUIRE(samples->state && samples->policy && samples->player && samples->value && samples->fstate, AGPU_ERR_INVALID, "null sample array");
     NvtxRange nv_loop(duel ? "agpu_duel" : "agpu_selfplay");
     while (L > 0) {

@@ -8,12 +8,13 @@
 //   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves, 128 games per tile.  Two tiles (129..256 games): 8 warps
 //                  per tile — TMEM lane quarter w%4, two 32-column slices each — with their own MMA issuer, tile 1 trailing tile 0 by one
 //                  MMA phase so that one tile's epilogue runs under the other's MMAs.  One tile: all 16 warps on it, one slice each.
-//                  The fp32 residual stream lives in TMEM (ordinary orientation) or in registers (swapped orientation); weights stream
+//                  The fp32 residual stream lives in registers (a thread owns the same row and columns in every layer); weights stream
 //                  global -> shared through a bulk-copy ring that never drains between rollouts.
 //                  (Measured alternatives, B200: all 16 warps alternating between the two tiles — 32 k cycles per rollout against 25 k,
 //                  because issuing a layer's eight tcgen05.mma occupies the issuing warp for 600-1200 cycles and the other 15 wait for
 //                  its share of the epilogue; the same with a 17th, issue-only warp — the register file then holds 20 warps x 96
-//                  registers and the search phases pay for it.)
+//                  registers and the search phases pay for it; two independent 256-thread CTAs of one tile each per SM, rounds 1 and 2 —
+//                  2.22 ms per full-load ply against 2.13: the co-resident CTAs do not hide each other's phases.)
 // Games of a CTA depend on each other only through their shared GEMM tile, so there is no grid-wide barrier and no kernel boundary
 // inside a ply: the per-rollout cost is the on-chip critical path instead of three launches plus their tails.
 #pragma once
@@ -37,27 +38,21 @@ using namespace tc;
 // NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
-// TH = 256 (with NT = 1): the PAIRED configuration — one tile, 8 warps, half the shared memory and a quarter of the tensor memory, so that
-// TWO CTAs of <= 128 games share an SM and drift out of phase: one's network chain (a latency chain that leaves most issue slots and
-// the load/store path idle) runs under the other's search phases.
-template <class G, int NT, int TH = 512> struct FCfg {
-  static constexpr int THREADS = TH;
-  static constexpr bool PAIRED = (NT == 1 && TH == 256);
-  static constexpr int WPT = (TH / 32) / NT;                           // warps per tile
+template <class G, int NT> struct FCfg {
+  static constexpr int THREADS = 512;
+  static constexpr int WPT = 16 / NT;                                  // warps per tile
   static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
-  static constexpr int GAMES = PAIRED ? 120 : NT * TC_TILE_M;          // games per CTA (capacity; paired: what fits twice in an SM's shared memory)
+  static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
   static constexpr int STAGES = NT == 1 ? 2 : 3;
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * ITEMS_PER_GAME + 2 + 2 * PATH_SMEM_DEPTH;
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
-  static constexpr int TREE_BYTES = (NT == 1 && !PAIRED) ? 64 * 1024 : 0;
+  static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
-  // tensor memory: 128 accumulator columns per tile (the fp32 residual stream is in registers); the small-batch kernel takes all 512
-  // columns and, in the swapped orientation, keeps the trunk weights — the A operand there — resident in columns 64..511
-  // (TW_COL0 + 64 per layer)
-  static constexpr int TMEM_COLS = PAIRED ? 128 : 512;
+  // tensor memory: 128 accumulator columns per tile (the fp32 residual stream is in registers); the small-batch kernel, in the swapped
+  // orientation, keeps the trunk weights — the A operand there — resident in columns 64..511 (TW_COL0 + 64 per layer)
+  static constexpr int TMEM_COLS = 512;
   static constexpr int TW_COL0 = 64, TW_MAX_LAYERS = 7;
-  static_assert(SMEM <= (PAIRED ? (228 * 1024 - 2 * 1024) / 2 : 227 * 1024), "shared memory per CTA (1 KB per resident CTA is reserved)");
-  static_assert(TH == 512 || PAIRED, "512 threads, or 256 for the paired one-tile configuration");
+  static_assert(SMEM <= 227 * 1024, "shared memory per CTA");
 };
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -149,12 +144,12 @@ AG_D long long clock_after_barrier(const void* smem_word) {
   return clock64() + (long long)(d & 0u);
 }
 
-template <class G, int FMT, int NT, int TH = 512>
-__global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+template <class G, int FMT, int NT>
+__global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   typedef Layout<G> Lay;
-  typedef FCfg<G, NT, TH> C;
+  typedef FCfg<G, NT> C;
   typedef typename G::State State;
-  constexpr bool SMALL = NT == 1 && !C::PAIRED;                        // the small-batch kernel: swapped orientation, node cache
+  constexpr bool SMALL = NT == 1;                                      // the small-batch kernel: swapped orientation, node cache
   constexpr int W = Lay::W;
   constexpr int STAGES = C::STAGES;
   static_assert(Lay::FAST && G::Geo::NC == 1 && 2 * G::VS <= TC_N, "fused ply kernel: small boards only");
@@ -419,7 +414,7 @@ __global__ void __launch_bounds__(TH, TH == 256 ? 2 : 1) ply_kernel(SearchParams
     if (dbg_on && threadIdx.x == 0) { const long long c = clock64(); t_ph[3] += c - t_mark; t_mark = c; }
 
     // ================= network phase =================
-    const bool obs = AG_TRACE >= 2 && dbg_on && threadIdx.x == TH / 2;    // development trace: a non-issuing warp's view of the network phase
+    const bool obs = AG_TRACE >= 2 && dbg_on && threadIdx.x == 256;    // development trace: a non-issuing warp's view of the network phase
     long long ob0 = 0;
     if (obs) ob0 = clock_after_barrier(s_next);
     {

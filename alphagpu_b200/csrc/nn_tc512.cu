@@ -204,6 +204,7 @@ __global__ void __maxnreg__(W5_MAXREG) tc_mlp512_kernel(Tc512Args T, NNInput I, 
         // The tensor-memory load of chunk cb + 1 is in flight while chunk cb is processed (tcgen05.wait::ld waits for ALL outstanding
         // loads: without the double buffer the load latency is exposed eight times per layer).
         uint32_t v[2][16];
+        const f32x2 half2 = pack2f(0.5f, 0.5f);
         tmem_ld16(tmem_row, v[0]);
 #pragma unroll
         for (int cb = 0; cb < 8; cb++) {
@@ -218,9 +219,12 @@ __global__ void __maxnreg__(W5_MAXREG) tc_mlp512_kernel(Tc512Args T, NNInput I, 
           uint32_t nw[8];
 #pragma unroll
           for (int e = 0; e < 8; e++) {
+            // b + relu(a) as fma(a + |a|, 0.5, b): a + |a| is 2 relu(a) exactly and the fma rounds once, like the add — FMA-pipe
+            // instructions only (an FADD per column, a packed FFMA per pair) instead of an FMNMX and an FADD per column
             const float2 o = unpack2<FMT>(ow[e]);
-            const float h0 = o.x + fmaxf(__uint_as_float(v[b][2 * e]), 0.f);
-            const float h1 = o.y + fmaxf(__uint_as_float(v[b][2 * e + 1]), 0.f);
+            const float a0 = __uint_as_float(v[b][2 * e]), a1 = __uint_as_float(v[b][2 * e + 1]);
+            float h0, h1;
+            unpack2f(fma2(pack2f(__fadd_rn(a0, fabsf(a0)), __fadd_rn(a1, fabsf(a1))), half2, pack2f(o.x, o.y)), h0, h1);
             nw[e] = pack2<FMT>(h0, h1);
           }
           *reinterpret_cast<uint4*>(p0) = make_uint4(nw[0], nw[1], nw[2], nw[3]);

@@ -64,27 +64,6 @@ def test_fused_ply_kernel_selfplay_bit_exact_vs_oracle(min_gpc, games, monkeypat
     assert_samples_equal(smp, osmp, res, ores, stats, ost, f"min_gpc={min_gpc}")
 
 
-# the paired configuration (two 256-thread CTAs per SM, fused.cuh FCfg<G, 1, 256>): forced through AGPU_FUSED_PAIR_MIN for small grids —
-# full CTAs of 120 games, half-filled ones, a ragged last CTA
-PAIRED_CASES = [(16, 150), (128, 300), (240, 600), (200, 333)]
-
-
-@pytest.mark.parametrize("min_gpc,games", PAIRED_CASES)
-def test_fused_paired_configuration_bit_exact_vs_oracle(min_gpc, games, monkeypatch):
-    monkeypatch.setenv("AGPU_FUSED_MIN_GPC", str(min_gpc))
-    monkeypatch.setenv("AGPU_FUSED_PAIR_MIN", "16")
-    name, R = "connect4", 64
-    ospec = oracle.Spec(*GAME_SPECS[name])
-    pnet, onet = make_exact_nets(GAME_SPECS[name], 128, 6, seed=12)
-    ctx = ctx_for(name, R, games, 128, 6)
-    ctx.set_weights(pnet)
-    res, stats, smp = ctx.selfplay(R, games, cpuct=1.5, seed=77, uid_base=5)
-    ctx.close()
-    osmp = oracle.Samples(ospec, games * ospec.maxLen)
-    ores, ost = oracle.selfplay(ospec, onet, R, games, cpuct=1.5, seed=77, uid_base=5, samples=osmp, nn_mode=oracle.Net.FP32)
-    assert_samples_equal(smp, osmp, res, ores, stats, ost, f"paired, min_gpc={min_gpc}")
-
-
 @pytest.mark.parametrize("nn_mode", [FP16_TC, BF16_TC])
 def test_fused_ply_kernel_config2_full_size_bit_exact_vs_oracle(nn_mode):
     """BASELINE config 2 at full size — Connect4, DenseNet 128x6, 64 rollouts, 32768 games — through the benchmarked kernel, held to
