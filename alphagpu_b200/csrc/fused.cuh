@@ -35,6 +35,7 @@ using namespace tc;
 #endif
 
 
+
 // NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
 // the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
 // cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
@@ -275,22 +276,26 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
 
   // one thread per game for the descent: the game's uid and node count stay in its registers for the whole ply; the root's state and the
   // first Philox block of the coming descent wait in shared memory
-  const bool has_game = (int)threadIdx.x < count;
-  const unsigned game_mask = __ballot_sync(0xffffffffu, has_game);      // the lanes of this warp that descend
-  const int my_g = g0 + (int)threadIdx.x;
+  // Up to 112 games per CTA they are dealt round-robin to the warps (local game lane * 16 + warp), so that all 16 warps descend: the
+  // phase lasts as long as the deepest game of the CTA, and with a few warps of 32 games its levels take longer (B200, per ply:
+  // -3..4 % below 12 k live games, +2 % at full load, where the packed assignment stays)
+  const int my_gl = (SMALL && gpc <= 112) ? lane * (C::THREADS / 32) + warp : (int)threadIdx.x;
+  const bool has_game = my_gl < count;
+  const unsigned game_mask = __ballot_sync(0xffffffffu, has_game);      // the lanes of this warp that descend (a prefix of the warp)
+  const int my_g = g0 + my_gl;
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
   if (has_game) {
-    SH.root[threadIdx.x] = *reinterpret_cast<const State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
-    SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
-    SH.d[threadIdx.x] = 0;
-    SH.ovf[threadIdx.x] = 0;
+    SH.root[my_gl] = *reinterpret_cast<const State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
+    SH.rnd[my_gl] = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
+    SH.d[my_gl] = 0;
+    SH.ovf[my_gl] = 0;
     if (SMALL) {
       // fill the node cache with the nodes that exist when the ply starts (the root alone after root_reset); read back only by this thread
       typedef CacheSlot<Lay::APAD> CS;
       const char* gb = P.tree + (size_t)my_g * P.game_stride;
       for (int nd = 0; nd < min(my_nn, SH.nc_nodes); nd++) {
-        unsigned char* sl = node_cache_slot<G, true>(SH, (int)threadIdx.x, nd);
+        unsigned char* sl = node_cache_slot<G, true>(SH, my_gl, nd);
         const char* rec = gb + (size_t)nd * Lay::REC;
         *reinterpret_cast<uint2*>(sl) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_HDR);
         for (int c = 0; c < Lay::APAD / 8; c++) *reinterpret_cast<uint2*>(sl + CS::OFF_CHILD + 8 * c) = *reinterpret_cast<const uint2*>(rec + Lay::OFF_CHILD + 8 * c);
@@ -391,8 +396,8 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         __syncwarp();
         if (dbg_on && lane == 0) atomicAdd(&s_next[3], 1);                // ... and finished
       }
-      if (has_game && SH.ovf[threadIdx.x] < SH.d[threadIdx.x]) {       // the list was full: this game backs up the rest of its path itself
-        const int gl = (int)threadIdx.x;
+      if (has_game && SH.ovf[my_gl] < SH.d[my_gl]) {                   // the list was full: this game backs up the rest of its path itself
+        const int gl = my_gl;
         const LeafEval E = leaf_eval1<G>(SH, gl);
         for (int jj = SH.ovf[gl]; jj < SH.d[gl]; jj++)
           backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, nullptr, SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     SH.lv_cnt = s_lvcnt + (k & 1);
     const long long w_t1 = dbg_on ? clock64() : 0;                      // development trace: per-warp time in the descent
     if (dbg_on && has_game && lane == 0 && s_next[2] != s_next[3]) T.dbg[blockIdx.x * 128 + 7] += 1;   // a descent started while a pool unit was still running
-    if (has_game) select_game1<G, SMALL>(P, my_g, (int)threadIdx.x, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (AG_TRACE >= 2 && dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 128 + 8 : nullptr);
+    if (has_game) select_game1<G, SMALL>(P, my_g, my_gl, SH, my_uid, my_nn, k, last, S.seed, S.ply, game_mask, (AG_TRACE >= 2 && dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 128 + 8 : nullptr);
     const long long w_d1 = dbg_on ? clock64() - w_t1 : 0;
     named_bar_sync(1, C::THREADS);
     if (dbg_on && lane == 0) T.dbg[blockIdx.x * 128 + 48 + warp] += w_d1;
@@ -478,8 +483,8 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         // the weights STAGES - 1 layers ahead are requested by a lane that would otherwise just wait for this layer's MMAs (on the
         // issuer the request sat on the critical path: 2 k cycles per rollout)
         if (!ts_mode && threadIdx.x == 32 && wll + STAGES - 1 < total_layers) load_layer(wll + STAGES - 1);
-        // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run (the game threads all belong to tile 0)
-        if (l == 0 && has_game) SH.rnd[threadIdx.x] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
+        // the Philox block of depths 0..3 of the NEXT descent, while the first MMAs run
+        if (l == 0 && has_game) SH.rnd[my_gl] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
         mbar_wait(bar_done + 8 * t, wll & 1);
         tc_fence_after();
         if (obs) { const long long c = clock64(); T.dbg[blockIdx.x * 128 + 66 + l] += c - ob0; ob0 = c; }
@@ -534,6 +539,8 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           tc_fence_before();
         }
       }
+    } else if (has_game) {                                             // (a game thread in a warp of the idle tile)
+      SH.rnd[my_gl] = philox4x32_10(my_uid, S.ply, (u32)(k + 1), 0u, (u32)S.seed, (u32)(S.seed >> 32));
     }
     wl += nlayers;
     named_bar_sync(1, C::THREADS);                                     // the outputs are visible to the search phase
