@@ -33,6 +33,12 @@ using namespace tc;
 #ifndef AG_TRACE
 #define AG_TRACE 0
 #endif
+#ifndef AG_STAGES2
+#define AG_STAGES2 2
+#endif
+#ifndef AG_TREE_KB
+#define AG_TREE_KB 64
+#endif
 
 
 
@@ -44,10 +50,10 @@ template <class G, int NT> struct FCfg {
   static constexpr int WPT = 16 / NT;                                  // warps per tile
   static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
-  static constexpr int STAGES = NT == 1 ? 2 : 3;
+  static constexpr int STAGES = NT == 1 ? 2 : AG_STAGES2;
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * ITEMS_PER_GAME + 2 + 2 * PATH_SMEM_DEPTH;
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
-  static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
+  static constexpr int TREE_BYTES = NT == 1 ? AG_TREE_KB * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
   // tensor memory: 128 accumulator columns per tile (the fp32 residual stream is in registers); the small-batch kernel, in the swapped
   // orientation, keeps the trunk weights — the A operand there — resident in columns 64..511 (TW_COL0 + 64 per layer)
@@ -194,8 +200,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   SH.lv_cnt = s_lvcnt;
   SH.leaf = reinterpret_cast<uint8_t*>(SH.lv_item + ITEMS_PER_GAME * C::GAMES);
   SH.ovf = SH.leaf + C::GAMES;
-  SH.pn = SH.ovf + C::GAMES;
-  SH.pm = SH.pn + C::GAMES * PATH_SMEM_DEPTH;
+  SH.path = reinterpret_cast<uint16_t*>(SH.ovf + C::GAMES);
   static_assert(sizeof(State) % 8 == 0 && sizeof(Philox4) == 16 && sizeof(NodeHdr) == 8, "hand-off layout");
   // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
   // the search phase reads the outputs in between
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
             const int gl = item & 0xFF, jj = item >> 8;
             const LeafEval E = leaf_eval1<G>(SH, gl);
             backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, (AG_TRACE >= 2 && dbg_on && threadIdx.x == 0) ? T.dbg + blockIdx.x * 128 + 8 : nullptr,
-                           SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
+                           SH.path + gl * PATH_SMEM_DEPTH,
                            SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
           }
         } else {
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
         const int gl = my_gl;
         const LeafEval E = leaf_eval1<G>(SH, gl);
         for (int jj = SH.ovf[gl]; jj < SH.d[gl]; jj++)
-          backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, nullptr, SH.pn + gl * PATH_SMEM_DEPTH, SH.pm + gl * PATH_SMEM_DEPTH,
+          backup_item<G>(P, g0 + gl, jj, SH.d[gl], E, 0, S.cpuct, nullptr, SH.path + gl * PATH_SMEM_DEPTH,
                          SH.nc_nodes > 0 ? SH.nc_base + (size_t)gl * SH.nc_nodes * CacheSlot<Lay::APAD>::BYTES : nullptr, SH.nc_nodes);
       }
       const long long w_d0 = dbg_on ? clock64() - w_t0 : 0;

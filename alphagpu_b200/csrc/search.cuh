@@ -153,8 +153,8 @@ struct RolloutShared {
   int out_tile_stride;       // (floats) the rows of a 128-game tile live in that tile's idle A-operand buffer
   int* d;                    // [GAMES] path length
   uint8_t* leaf;             // [GAMES]
-  uint8_t* pn;               // [GAMES][PATH_SMEM_DEPTH] path nodes
-  uint8_t* pm;               // [GAMES][PATH_SMEM_DEPTH] path moves
+  uint16_t* path;            // [GAMES][PATH_SMEM_DEPTH] path entries: node | move << 8 (one request per level for the descent and per item
+                             // for the backup — the search phases are bound by the number of load/store requests)
   int* lv_cnt;               // items of the last descent: entries reserved in lv_item (may exceed lv_cap)
   uint16_t* lv_item;         // [lv_cap] item = local game | path index << 8
   int lv_cap;                // capacity of the item list
@@ -790,7 +790,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
 // literal chain.  π̄ is not re-solved after the last rollout: nobody reads it (policy_final is the root policy of the last DESCENT, :443).
 template <class G>
 AG_D void backup_item(const SearchParams& P, const int g, const int jj, const int d, const LeafEval& E, int last_rollout, const float cpuct,
-                      long long* tr = nullptr, const uint8_t* s_pn = nullptr, const uint8_t* s_pm = nullptr,
+                      long long* tr = nullptr, const uint16_t* s_path = nullptr,
                       unsigned char* s_cache_row = nullptr, const int nc_nodes = 0) {
   const long long tr0 = tr ? clock64() : 0;
   typedef Layout<G> Lay;
@@ -803,10 +803,10 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
     {
       {
         const int flips = d - 1 - jj;
-        // s_pn / s_pm: this game's path in shared memory (fused kernel), PATH_SMEM_DEPTH entries
-        const bool in_smem = s_pn != nullptr && jj < PATH_SMEM_DEPTH;
-        const int nd = in_smem ? s_pn[jj] : P.path_node[(size_t)g * P.R + jj];
-        const int mv = in_smem ? s_pm[jj] : P.path_move[(size_t)g * P.R + jj];
+        // s_path: this game's path in shared memory (fused kernel), PATH_SMEM_DEPTH entries of node | move << 8
+        int nd, mv;
+        if (s_path != nullptr && jj < PATH_SMEM_DEPTH) { const int e = s_path[jj]; nd = e & 0xFF; mv = e >> 8; }
+        else { nd = P.path_node[(size_t)g * P.R + jj]; mv = P.path_move[(size_t)g * P.R + jj]; }
         char* nrec = gbase + (size_t)nd * REC;
         float p[AP], q[AP], pol[AP];
         int vis[AP], ch[AP], ord[AP];
@@ -824,15 +824,25 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
           for (int e = 0; e < 4; e++) { vis[8 * c + 2 * e] = (int)(w4[e] & 0xFFFFu); vis[8 * c + 2 * e + 1] = (int)(w4[e] >> 16); }
         }
+        uint32_t hw;                                                                   // parent | action | nchild | flags
+        if (AP == 8) {                                                                 // header + child ids: one 16-byte request
+          const uint4 hc = hot_ld_u4(nrec + Lay::OFF_HDR);
+          const uint2 ov = hot_ld_u2(nrec + Lay::OFF_ORDER);
+          hw = hc.x;
+          const uint32_t cw[2] = {hc.z, hc.w}, ow[2] = {ov.x, ov.y};
 #pragma unroll
-        for (int c = 0; c < AP / 8; c++) {          // child bytes then order bytes, AP bytes each, contiguous
-          const uint2 cv = hot_ld_u2(nrec + Lay::OFF_CHILD + 8 * c);
-          const uint2 ov = hot_ld_u2(nrec + Lay::OFF_ORDER + 8 * c);
-          const uint32_t cw[2] = {cv.x, cv.y}, ow[2] = {ov.x, ov.y};
+          for (int e = 0; e < 8; e++) { ch[e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
+        } else {
 #pragma unroll
-          for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
+          for (int c = 0; c < AP / 8; c++) {          // child bytes then order bytes, AP bytes each, contiguous
+            const uint2 cv = hot_ld_u2(nrec + Lay::OFF_CHILD + 8 * c);
+            const uint2 ov = hot_ld_u2(nrec + Lay::OFF_ORDER + 8 * c);
+            const uint32_t cw[2] = {cv.x, cv.y}, ow[2] = {ov.x, ov.y};
+#pragma unroll
+            for (int e = 0; e < 8; e++) { ch[8 * c + e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[8 * c + e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
+          }
+          hw = *reinterpret_cast<const uint32_t*>(nrec + Lay::OFF_HDR);
         }
-        const uint32_t hw = *reinterpret_cast<const uint32_t*>(nrec + Lay::OFF_HDR);   // parent | action | nchild | flags
         const int nchild = (int)((hw >> 16) & 0xFFu);
         const bool prior_box = ((hw >> 24) & F_PRIOR_BOX) != 0;
         // running mean of the child's value from this node's point of view (:319-320)
@@ -909,18 +919,24 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
   typename G::State cur = SH.root[gl];
   int best = 0, nchild = 0;
   bool create = false;
+  u64 cw0 = 0, cw1 = 0;                                                              // child ids of the current node, 8 per word
 
   while (true) {
     char* rec = gbase + (size_t)node * REC;
     // header, child ids and π̄ are the record's first bytes: every load of the level is issued before the flag is tested
     static_assert(AP == 8 || AP == 16, "child ids are read as one or two 64-bit words");
-    u64 cw0, cw1 = 0;
     float pol[AP];
     const unsigned char* sl = node_cache_slot<G, CACHE>(SH, gl, node);                 // this node's cache entry, if it has one
     if (CACHE && sl != nullptr) {
-      hw = *reinterpret_cast<const uint2*>(sl);
-      const uint2 cv = *reinterpret_cast<const uint2*>(sl + CS::OFF_CHILD);
-      cw0 = (u64)cv.x | ((u64)cv.y << 32);
+      if (AP == 8) {                                                                   // header + child ids: one 16-byte request
+        const uint4 hc = *reinterpret_cast<const uint4*>(sl);
+        hw = make_uint2(hc.x, hc.y);
+        cw0 = (u64)hc.z | ((u64)hc.w << 32);
+      } else {
+        hw = *reinterpret_cast<const uint2*>(sl);
+        const uint2 cv = *reinterpret_cast<const uint2*>(sl + CS::OFF_CHILD);
+        cw0 = (u64)cv.x | ((u64)cv.y << 32);
+      }
       if (AP == 16) {
         const uint2 cv1 = *reinterpret_cast<const uint2*>(sl + CS::OFF_CHILD + 8);
         cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
@@ -932,9 +948,17 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
       }
     } else {
       // child ids, 8 per 64-bit word (plain scalars: an indexed array would live in local memory, and its store would stall on the load)
-      hw = hot_ld_u2(rec + Lay::OFF_HDR);
-      const uint2 cv = hot_ld_u2(rec + Lay::OFF_CHILD);
-      cw0 = (u64)cv.x | ((u64)cv.y << 32);
+      // (the search phases are bound by the number of load/store requests: header and child ids, adjacent in the record, travel together)
+      if (AP == 8) {
+        static_assert(AP != 8 || (Lay::OFF_HDR % 16 == 0 && Lay::OFF_CHILD == Lay::OFF_HDR + 8 && Lay::REC % 16 == 0), "header + child ids as one 16-byte load");
+        const uint4 hc = hot_ld_u4(rec + Lay::OFF_HDR);
+        hw = make_uint2(hc.x, hc.y);
+        cw0 = (u64)hc.z | ((u64)hc.w << 32);
+      } else {
+        hw = hot_ld_u2(rec + Lay::OFF_HDR);
+        const uint2 cv = hot_ld_u2(rec + Lay::OFF_CHILD);
+        cw0 = (u64)cv.x | ((u64)cv.y << 32);
+      }
       if (AP == 16) {
         const uint2 cv1 = hot_ld_u2(rec + Lay::OFF_CHILD + 8);
         cw1 = (u64)cv1.x | ((u64)cv1.y << 32);
@@ -975,7 +999,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     if (best < 0) best = 0;
     if (tr && depth == 0) trC = clock64() + (best & 0);
     if (last_rollout || depth >= PATH_SMEM_DEPTH) { pnode[depth] = (uint8_t)node; pmove[depth] = (uint8_t)best; }
-    if (depth < PATH_SMEM_DEPTH) { SH.pn[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)node; SH.pm[gl * PATH_SMEM_DEPTH + depth] = (uint8_t)best; }
+    if (depth < PATH_SMEM_DEPTH) SH.path[gl * PATH_SMEM_DEPTH + depth] = (uint16_t)(node | (best << 8));
     const int c = (int)(((AP == 16 && best >= 8 ? cw1 : cw0) >> (8 * (best & 7))) & 0xFFu);
     if (c == 0) { create = true; break; }                                              // the child does not exist yet: allocate it below
     node = c - 1;                                                                      // :192
@@ -988,23 +1012,31 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     char* rec = gbase + (size_t)node * REC;
     nn += 1;
     const int c = nn;
-    *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
+    if (AP == 8) {                                   // the parent's header (child count) and child ids are in registers: one 16-byte store
+      const u64 ncw = cw0 | ((u64)(uint32_t)c << (8 * best));
+      *reinterpret_cast<uint4*>(rec + Lay::OFF_HDR) = make_uint4((hw.x & 0xFF00FFFFu) | ((uint32_t)(nchild + 1) << 16), hw.y, (uint32_t)ncw, (uint32_t)(ncw >> 32));
+    } else {
+      *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
+      reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
+    }
     *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
-    reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
     const typename G::State ns = G::play(cur, best + 1);
     int res = 0;
     const bool term = G::is_over(ns, res);
     char* nrec = gbase + (size_t)(c - 1) * REC;
 #pragma unroll
     for (int k = 0; k < AP / 4; k++) *reinterpret_cast<float4*>(nrec + Lay::OFF_Q + 16 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
+    const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
 #pragma unroll
-    for (int k = 0; k < AP / 8; k++) {
-      *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
-      *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
+    for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
+    if (AP == 8) {                                   // header + (empty) child ids: one 16-byte store
+      *reinterpret_cast<uint4*>(nrec + Lay::OFF_HDR) = make_uint4((uint32_t)nhw, (uint32_t)(nhw >> 32), 0u, 0u);
+    } else {
+#pragma unroll
+      for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
+      hdr_store(nrec + Lay::OFF_HDR, nhw);
     }
     state_store(nrec + Lay::OFF_STATE, ns);
-    const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
-    hdr_store(nrec + Lay::OFF_HDR, nhw);
     if (CACHE) {
       if (unsigned char* csl = node_cache_slot<G, CACHE>(SH, gl, node)) {              // the parent's entry: child id and child count
         csl[CS::OFF_CHILD + best] = (uint8_t)c;
@@ -1017,12 +1049,12 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
       }
     }
     SH.state[gl] = ns;
-    hdr_store(&SH.hdr[gl], nhw);
+    hdr_store(&SH.hdr[gl], nhw | ((u64)(uint8_t)(int8_t)(ns.player * res) << 40));   // + player * result for the backup items (leaf_eval1)
     node = c - 1;
     depth += 1;
   } else {
     SH.state[gl] = cur;
-    *reinterpret_cast<uint2*>(&SH.hdr[gl]) = hw;
+    *reinterpret_cast<uint2*>(&SH.hdr[gl]) = make_uint2(hw.x, (hw.y & 0xFFu) | ((uint32_t)(uint8_t)(int8_t)(cur.player * (int8_t)(hw.y & 0xFFu)) << 8));
   }
   if (tr) { tr[4] += clock64() + (node & 0) - tr0; tr[5] += depth; tr[8] += trA - tr0; tr[9] += trB - tr0; tr[10] += trC - tr0; tr[6] += trD - tr0; }
   SH.leaf[gl] = (uint8_t)node;
@@ -1161,7 +1193,7 @@ AG_D LeafEval leaf_eval1(const RolloutShared<G>& SH, const int gl) {
   E.term = (h.flags & F_TERMINAL) ? 1 : 0;
   E.v = SH.out[(gl >> 7) * SH.out_tile_stride + (gl & 127) * Lay::OUTS + G::A];
   E.parent = h.parent; E.action = h.action;
-  E.value0_d = (double)(1 + (int)(int8_t)(SH.state[gl].player * h.result)) * 0.5;
+  E.value0_d = (double)(1 + (int)(int8_t)h.pad[0]) * 0.5;                           // pad[0] of the hand-off copy: player * result (select_game1)
   return E;
 }
 
