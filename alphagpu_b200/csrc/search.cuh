@@ -82,6 +82,10 @@ struct Layout {
   // a node's statistics change only when a backup passes through it (sticky `uptodate`, mcts_gpu.jl:114,321) and the solve is a
   // pure function of them.  Large action sets keep the cooperative solve-at-descent (the network dominates there).
   static constexpr bool FAST = (A <= 9);
+  // FAST records with at most 7 actions keep the creation order of the children in the header's spare bytes — slot k's 1-based action in
+  // bits 40 + 3k of the header word — so that header, order and child ids are one 16-byte access for the backup and one 16-byte store
+  // when a child is created (the order byte array of the other layouts stays unused)
+  static constexpr bool ORD_IN_HDR = FAST && A <= 7;
   static constexpr int SB = FAST ? 256 : AG_BLOCK_BIG;            // threads per block of select / expand+backup / step kernels
   static constexpr int SB_MIN = AG_MINBLOCKS * 256 / SB;          // resident blocks per SM they are compiled for
   static constexpr int a16(int x) { return (x + 15) / 16 * 16; }
@@ -627,8 +631,13 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
         }
       }
       if (l == 0) {
-        *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + h.nchild) = (uint8_t)(best + 1);
-        reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(h.nchild + 1);
+        if constexpr (Lay::ORD_IN_HDR) {
+          const u64 w = *reinterpret_cast<const u64*>(rec + Lay::OFF_HDR);
+          hdr_store(rec + Lay::OFF_HDR, (w & ~(0xFFull << 16)) | ((u64)(h.nchild + 1) << 16) | ((u64)(best + 1) << (40 + 3 * h.nchild)));
+        } else {
+          *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + h.nchild) = (uint8_t)(best + 1);
+          reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(h.nchild + 1);
+        }
         *reinterpret_cast<typename G::State*>(nrec + Lay::OFF_STATE) = ns;
         hdr_store(nrec + Lay::OFF_HDR, hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res));
       }
@@ -825,13 +834,12 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
           for (int e = 0; e < 4; e++) { vis[8 * c + 2 * e] = (int)(w4[e] & 0xFFFFu); vis[8 * c + 2 * e + 1] = (int)(w4[e] >> 16); }
         }
         uint32_t hw;                                                                   // parent | action | nchild | flags
-        if (AP == 8) {                                                                 // header + child ids: one 16-byte request
+        if (Lay::ORD_IN_HDR) {                                                         // header (+ creation order) + child ids: one 16-byte request
           const uint4 hc = hot_ld_u4(nrec + Lay::OFF_HDR);
-          const uint2 ov = hot_ld_u2(nrec + Lay::OFF_ORDER);
           hw = hc.x;
-          const uint32_t cw[2] = {hc.z, hc.w}, ow[2] = {ov.x, ov.y};
+          const uint32_t cw[2] = {hc.z, hc.w};
 #pragma unroll
-          for (int e = 0; e < 8; e++) { ch[e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[e] = (int)((ow[e >> 2] >> (8 * (e & 3))) & 0xFFu); }
+          for (int e = 0; e < 8; e++) { ch[e] = (int)((cw[e >> 2] >> (8 * (e & 3))) & 0xFFu); ord[e] = e < 7 ? (int)((hc.y >> (8 + 3 * e)) & 7u) : 0; }
         } else {
 #pragma unroll
           for (int c = 0; c < AP / 8; c++) {          // child bytes then order bytes, AP bytes each, contiguous
@@ -1012,14 +1020,16 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     char* rec = gbase + (size_t)node * REC;
     nn += 1;
     const int c = nn;
-    if (AP == 8) {                                   // the parent's header (child count) and child ids are in registers: one 16-byte store
+    uint4 phc = make_uint4(0, 0, 0, 0);
+    if (Lay::ORD_IN_HDR) {                           // the parent's header (child count, creation order) and child ids are in registers: one 16-byte store
       const u64 ncw = cw0 | ((u64)(uint32_t)c << (8 * best));
-      *reinterpret_cast<uint4*>(rec + Lay::OFF_HDR) = make_uint4((hw.x & 0xFF00FFFFu) | ((uint32_t)(nchild + 1) << 16), hw.y, (uint32_t)ncw, (uint32_t)(ncw >> 32));
+      phc = make_uint4((hw.x & 0xFF00FFFFu) | ((uint32_t)(nchild + 1) << 16), hw.y | ((uint32_t)(best + 1) << (8 + 3 * nchild)), (uint32_t)ncw, (uint32_t)(ncw >> 32));
+      *reinterpret_cast<uint4*>(rec + Lay::OFF_HDR) = phc;
     } else {
       *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
       reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(nchild + 1);
+      *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
     }
-    *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + nchild) = (uint8_t)(best + 1);
     const typename G::State ns = G::play(cur, best + 1);
     int res = 0;
     const bool term = G::is_over(ns, res);
@@ -1029,7 +1039,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
 #pragma unroll
     for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
-    if (AP == 8) {                                   // header + (empty) child ids: one 16-byte store
+    if (Lay::ORD_IN_HDR) {                           // header + (empty) child ids: one 16-byte store
       *reinterpret_cast<uint4*>(nrec + Lay::OFF_HDR) = make_uint4((uint32_t)nhw, (uint32_t)(nhw >> 32), 0u, 0u);
     } else {
 #pragma unroll
@@ -1038,9 +1048,9 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
     }
     state_store(nrec + Lay::OFF_STATE, ns);
     if (CACHE) {
-      if (unsigned char* csl = node_cache_slot<G, CACHE>(SH, gl, node)) {              // the parent's entry: child id and child count
-        csl[CS::OFF_CHILD + best] = (uint8_t)c;
-        csl[2] = (uint8_t)(nchild + 1);                                                // NodeHdr::nchild
+      if (unsigned char* csl = node_cache_slot<G, CACHE>(SH, gl, node)) {              // the parent's entry: child id, child count, order
+        if (Lay::ORD_IN_HDR) *reinterpret_cast<uint4*>(csl) = phc;
+        else { csl[CS::OFF_CHILD + best] = (uint8_t)c; csl[2] = (uint8_t)(nchild + 1); }
       }
       if (unsigned char* nsl = node_cache_slot<G, CACHE>(SH, gl, c - 1)) {             // the new node's entry (π̄ is written by expand)
         hdr_store(nsl, nhw);
