@@ -732,7 +732,11 @@ struct EngineT : EngineBase {
           float f; uint16_t v16; uint8_t b8;
           if (out->prior) { memcpy(&f, rec + Lay::OFF_PRIOR + 4 * a, 4); out->prior[oa] = has_prior ? f : 0.f; }
           if (out->q) { memcpy(&f, rec + Lay::OFF_Q + 4 * a, 4); out->q[oa] = live ? f : 0.f; }
-          if (out->visits) { memcpy(&v16, rec + Lay::OFF_VIS + 2 * a, 2); out->visits[oa] = live ? (float)v16 : 0.f; }
+          if (out->visits) {
+            if (Lay::VIS_IN_PAD) { memcpy(&b8, rec + Lay::vis_byte(a), 1); v16 = b8; }
+            else memcpy(&v16, rec + Lay::OFF_VIS + 2 * a, 2);
+            out->visits[oa] = live ? (float)v16 : 0.f;
+          }
           if (out->child) { memcpy(&b8, rec + Lay::OFF_CHILD + a, 1); out->child[oa] = live ? b8 : 0; }
           if (out->order) {
             if (Lay::ORD_IN_HDR) { uint64_t w; memcpy(&w, rec + Lay::OFF_HDR, 8); b8 = a < 7 ? (uint8_t)((w >> (40 + 3 * a)) & 7u) : 0; }

@@ -86,6 +86,11 @@ struct Layout {
   // bits 40 + 3k of the header word — so that header, order and child ids are one 16-byte access for the backup and one 16-byte store
   // when a child is created (the order byte array of the other layouts stays unused)
   static constexpr bool ORD_IN_HDR = FAST && A <= 7;
+  // ... and the visit counts (one byte each: a game's tree has at most 255 nodes) in the eighth, unused slots of the q and prior vectors —
+  // actions 0..3 behind q, 4..6 behind prior — so that the backup needs no separate load for them.  Both slots are zero when the node
+  // is created (q) / expanded (prior), before any of its children can be visited.
+  static constexpr bool VIS_IN_PAD = ORD_IN_HDR;
+  static constexpr int vis_byte(int a) { return a < 4 ? OFF_Q_F + 28 + a : OFF_PRIOR_F + 24 + a; }   // (FAST offsets; VIS_IN_PAD only)
   static constexpr int SB = FAST ? 256 : AG_BLOCK_BIG;            // threads per block of select / expand+backup / step kernels
   static constexpr int SB_MIN = AG_MINBLOCKS * 256 / SB;          // resident blocks per SM they are compiled for
   static constexpr int a16(int x) { return (x + 15) / 16 * 16; }
@@ -826,12 +831,18 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
           p[4 * c] = pv.x; p[4 * c + 1] = pv.y; p[4 * c + 2] = pv.z; p[4 * c + 3] = pv.w;
           q[4 * c] = qv.x; q[4 * c + 1] = qv.y; q[4 * c + 2] = qv.z; q[4 * c + 3] = qv.w;
         }
+        if (Lay::VIS_IN_PAD) {
+          const uint32_t v03 = __float_as_uint(q[7]), v46 = __float_as_uint(p[7]);
 #pragma unroll
-        for (int c = 0; c < AP / 8; c++) {
-          const uint4 vv = hot_ld_u4(nrec + Lay::OFF_VIS + 16 * c);
-          const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+          for (int a = 0; a < 8; a++) vis[a] = a < 4 ? (int)((v03 >> (8 * a)) & 0xFFu) : a < 7 ? (int)((v46 >> (8 * (a - 4))) & 0xFFu) : 0;
+        } else {
 #pragma unroll
-          for (int e = 0; e < 4; e++) { vis[8 * c + 2 * e] = (int)(w4[e] & 0xFFFFu); vis[8 * c + 2 * e + 1] = (int)(w4[e] >> 16); }
+          for (int c = 0; c < AP / 8; c++) {
+            const uint4 vv = hot_ld_u4(nrec + Lay::OFF_VIS + 16 * c);
+            const uint32_t w4[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) { vis[8 * c + 2 * e] = (int)(w4[e] & 0xFFFFu); vis[8 * c + 2 * e + 1] = (int)(w4[e] >> 16); }
+          }
         }
         uint32_t hw;                                                                   // parent | action | nchild | flags
         if (Lay::ORD_IN_HDR) {                                                         // header (+ creation order) + child ids: one 16-byte request
@@ -871,7 +882,8 @@ AG_D void backup_item(const SearchParams& P, const int g, const int jj, const in
 #pragma unroll
         for (int a = 0; a < A; a++) if (a == mv) { q[a] = qnew; vis[a] = vold + 1; }
         *reinterpret_cast<float*>(nrec + Lay::OFF_Q + 4 * mv) = qnew;
-        *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * mv) = (uint16_t)(vold + 1);
+        if (Lay::VIS_IN_PAD) *reinterpret_cast<uint8_t*>(nrec + (mv < 4 ? Lay::OFF_Q + 28 + mv : Lay::OFF_PRIOR + 24 + mv)) = (uint8_t)(vold + 1);
+        else *reinterpret_cast<uint16_t*>(nrec + Lay::OFF_VIS + 2 * mv) = (uint16_t)(vold + 1);
         long long tr1 = 0;
         if (tr) { tr1 = clock64() + (__float_as_int(qnew) & 0); tr[0] += tr1 - tr0; }
         if (!last_rollout) {
@@ -1037,8 +1049,10 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
 #pragma unroll
     for (int k = 0; k < AP / 4; k++) *reinterpret_cast<float4*>(nrec + Lay::OFF_Q + 16 * k) = make_float4(0.f, 0.f, 0.f, 0.f);
     const u64 nhw = hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res);
+    if (!Lay::VIS_IN_PAD) {                          // (else the counts live in the zeroed q vector / the prior vector written by expand)
 #pragma unroll
-    for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
+      for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint4*>(nrec + Lay::OFF_VIS + 16 * k) = make_uint4(0, 0, 0, 0);
+    }
     if (Lay::ORD_IN_HDR) {                           // header + (empty) child ids: one 16-byte store
       *reinterpret_cast<uint4*>(nrec + Lay::OFF_HDR) = make_uint4((uint32_t)nhw, (uint32_t)(nhw >> 32), 0u, 0u);
     } else {
