@@ -2,7 +2,7 @@
 //
 // A CTA of 512 threads (16 warps x 128 registers) owns up to 256 games for the entire search of a ply and alternates, per rollout,
 //   search phase : ONE POOL of warp-sized work units drawn from a shared-memory counter — the (game, ancestor) items of backUp + the
-//                  α re-solve (search.cuh: backup_item), listed level by level by the descents that produced them, and the expansion of
+//                  α re-solve (search.cuh: backup_item), listed game by game by the descents that produced them, and the expansion of
 //                  the leaves (expand_game1), 32 games per unit — then, behind one barrier, the descent of the next rollout, one thread
 //                  per game (select_game1).  Everything a phase hands to the next lives in shared memory (RolloutShared).
 //   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves, 128 games per tile.  Two tiles (129..256 games): 8 warps
@@ -33,27 +33,21 @@ using namespace tc;
 #ifndef AG_TRACE
 #define AG_TRACE 0
 #endif
-#ifndef AG_STAGES2
-#define AG_STAGES2 2
-#endif
-#ifndef AG_TREE_KB
-#define AG_TREE_KB 64
-#endif
 
-
-
-// NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA), 3-stage weight ring.  NT = 1: the small-batch kernel of
-// the tail of a generation (<= 128 games per CTA): 2-stage ring, trunk layers in the swapped orientation up to 64 games, and a node
-// cache (search.cuh: CacheSlot) in the shared memory the second tile would have used.
+// NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA).  NT = 1: the small-batch kernel of the tail of a generation
+// (<= 128 games per CTA): trunk layers in the swapped orientation up to 64 games, and a node cache (search.cuh: CacheSlot) in the shared
+// memory the second tile would have used.  Both stream the weights through a 2-stage ring: the two-tile kernel then needs 162 KB of
+// shared memory, which leaves the SM 92 KB of L1 for the tree records instead of the 60 KB a third stage left (B200: -1 % per
+// generation; the search phases live on the number of load/store requests and on where they hit, see search.cuh).
 template <class G, int NT> struct FCfg {
   static constexpr int THREADS = 512;
   static constexpr int WPT = 16 / NT;                                  // warps per tile
   static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
   static constexpr int GAMES = NT * TC_TILE_M;                         // games per CTA (capacity)
-  static constexpr int STAGES = NT == 1 ? 2 : AG_STAGES2;
+  static constexpr int STAGES = 2;
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * ITEMS_PER_GAME + 2 + 2 * PATH_SMEM_DEPTH;
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
-  static constexpr int TREE_BYTES = NT == 1 ? AG_TREE_KB * 1024 : 0;
+  static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
   static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
   // tensor memory: 128 accumulator columns per tile (the fp32 residual stream is in registers); the small-batch kernel, in the swapped
   // orientation, keeps the trunk weights — the A operand there — resident in columns 64..511 (TW_COL0 + 64 per layer)

@@ -445,10 +445,11 @@ def main():
                      "share_of_step": dom_ms / total_ms, "sims_per_launch": pst["sims"] / classes[dom]["launches"],
                      "bytes_per_sim_basis": "SURVEY.md §8(d) B_sim at the measured d_bar (leaf operands and network outputs counted as HBM traffic although the "
                                             "per-ply kernel keeps them on chip: %d B/sim without them)" % round(per_sim["select"] + per_sim["expand_backup"] + per_sim["nn"]),
-                     "note": "not HBM-bound: see DESIGN.md §6 and profiles/ncu_dominant_kernel.json (full-load launch: issue slots 40 % busy, tensor pipe 11 %, "
-                             "DRAM 736 B per simulation; the search phases are bound by the SM's load/store pipe (one request per lane and 16 bytes), the network "
-                             "phase by epilogue issue slots and tcgen05.mma issue; ~60 % of a generation is spent in plies with more than 128 games per SM, ~37 % in "
-                             "the tail, where a rollout is a dependent chain whose length does not shrink with the number of live games"},
+                     "note": "not HBM-bound: see DESIGN.md §6 and profiles/ncu_dominant_kernel.json (full-load launch: issue slots 40 % busy, tensor pipe 14 %, "
+                             "DRAM 745 B per simulation; the search phases are bound by the number of load/store requests of the SM (one per lane and 16 bytes) and "
+                             "by where they hit, the network phase by epilogue issue slots and tcgen05.mma issue; 49 % of a generation is spent in plies with more "
+                             "than 128 games per SM, 24 % between 32 and 128, 27 % in the tail, where a rollout is a dependent chain whose length does not shrink "
+                             "with the number of live games"},
         "roofline_nn": {"kernel": nn_name, "bound": "tensor", "achieved": nn_tf, "peak": tflops, "unit": "TFLOP/s", "frac": nn_tf / tflops,
                         "flop_per_sim": f_sim, "share_of_step": nn_ms / total_ms},
         "kernel_ms": {k: round(v["ms"], 3) for k, v in classes.items()},
