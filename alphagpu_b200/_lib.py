@@ -90,6 +90,8 @@ SIGNATURES = {
     "agpu_profile": (C.c_int, [_VP, _I32]),
     "agpu_get_kernel_times": (C.c_int, [_VP, C.POINTER(KernelTimes), _I32]),
     "agpu_layout_info": (C.c_int, [_VP, C.POINTER(_I64), C.POINTER(_I64), C.POINTER(_I64)]),
+    "agpu_host_alloc": (C.c_int, [C.POINTER(_VP), _U64]),
+    "agpu_host_free": (C.c_int, [_VP]),
     "agpu_debug_expf": (C.c_int, [_VP, _VP, _I64, _VP, _I32]),
     "agpu_debug_fdiv_check": (C.c_int, [_U64, _U64, _VP]),
 }

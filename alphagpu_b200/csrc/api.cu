@@ -259,6 +259,13 @@ int agpu_get_kernel_times(agpu_ctx* ctx, agpu_kernel_times* out, int32_t reset) 
   CTX_OR_FAIL();
   return ctx->eng->kernel_times(out, reset);
 }
+int agpu_host_alloc(void** out, uint64_t bytes) {
+  if (!out || bytes == 0) return AGPU_ERR_INVALID;
+  *out = nullptr;
+  return cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable) == cudaSuccess ? AGPU_OK : AGPU_ERR_CUDA;
+}
+int agpu_host_free(void* p) { return (p == nullptr || cudaFreeHost(p) == cudaSuccess) ? AGPU_OK : AGPU_ERR_CUDA; }
+
 int agpu_layout_info(agpu_ctx* ctx, int64_t* node_bytes, int64_t* game_bytes, int64_t* lanes_per_game) {
   CTX_OR_FAIL();
   return ctx->eng->layout_info(node_bytes, game_bytes, lanes_per_game);

@@ -45,6 +45,42 @@ class PoolSample:
         return self.length if self.full else self.currentIndex
 
 
+class PinnedSamples:
+    """Page-locked sample arrays (agpu_host_alloc) of a fixed capacity, as numpy views: the `out=` argument of selfplay().  With them
+    agpu_selfplay streams the rows of a ply to the host while the next ply searches.  The views die with close()."""
+
+    FIELDS = ("state", "policy", "player", "value", "fstate", "game", "ply")
+
+    def __init__(self, lib, cap: int, VS: int, A: int, FS: int):
+        self.lib, self.cap, self._ptrs = lib, cap, []
+        shapes = dict(state=((cap, 2 * VS), np.int8), policy=((cap, A), np.float32), player=((cap,), np.int8), value=((cap,), np.float32),
+                      fstate=((cap, FS), np.int8), game=((cap,), np.int32), ply=((cap,), np.int32))
+        self.arrays = {}
+        for k in self.FIELDS:
+            shape, dt = shapes[k]
+            nbytes = max(1, int(np.prod(shape)) * np.dtype(dt).itemsize)
+            p = C.c_void_p()
+            rc = lib.agpu_host_alloc(C.byref(p), nbytes)
+            if rc != _lib.OK:
+                self.close()
+                raise _lib.AlphaGPUError(rc, "agpu_host_alloc failed")
+            self._ptrs.append(p)
+            buf = (C.c_char * nbytes).from_address(p.value)
+            self.arrays[k] = np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self):
+        self.arrays = {}
+        for p in self._ptrs:
+            self.lib.agpu_host_free(p)
+        self._ptrs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Context:
     """One `init(positions, visits)` (mcts_gpu.jl:350-357): the tree arrays for `ngames` games × `visits` nodes on one GPU."""
 
@@ -60,9 +96,19 @@ class Context:
         self.live = 0
 
     def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
+            self._pinned = None
         if getattr(self, "h", None):
             self.lib.agpu_destroy(self.h)
             self.h = None
+
+    def pinned_samples(self):
+        """Page-locked sample arrays sized for this context (ngames x maxLengthGame rows), allocated once and reused: pass them as
+        selfplay(out=...).  Their contents are overwritten by the next generation."""
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = PinnedSamples(self.lib, self.ngames * self.spec.maxLengthGame, self.VS, self.A, self.FS)
+        return self._pinned.arrays
 
     def __del__(self):
         try:
@@ -244,9 +290,18 @@ class MultiContext:
         self.h = h
 
     def close(self):
+        if getattr(self, "_pinned", None) is not None:
+            self._pinned.close()
+            self._pinned = None
         if getattr(self, "h", None):
             self.lib.agpu_multi_destroy(self.h)
             self.h = None
+
+    def pinned_samples(self):
+        """Page-locked sample arrays sized for this context, allocated once and reused (see Context.pinned_samples)."""
+        if getattr(self, "_pinned", None) is None:
+            self._pinned = PinnedSamples(self.lib, self.ngames * self.spec.maxLengthGame, self.VS, self.A, self.FS)
+        return self._pinned.arrays
 
     def __del__(self):
         try:
@@ -367,7 +422,9 @@ def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample
             ctx = MultiContext(spec, visits, ngames, actor.width, actor.blocks, ngpus, nn_mode=nn_mode)
         ctx.set_weights(actor, 0)
         noise = float(2.0 / spec.maxActions) if noise is None else noise
-        res, stats, out = ctx.selfplay(visits, ngames, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
+        # a context the caller keeps across generations brings page-locked sample arrays (the samples are copied into `buffer` right away)
+        pinned = ctx.pinned_samples() if (buffer is not None and not own and ctx.ngames >= ngames) else None
+        res, stats, out = ctx.selfplay(visits, ngames, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None, out=pinned)
         if buffer is not None:
             buffer.push_block(out["state"], out["policy"], out["player"], out["value"], out["fstate"])
         if own:
@@ -391,11 +448,12 @@ def mcts(actor: SNetwork2, visits: int, ngames: int, buffer: Optional[PoolSample
             ctx = init(spec, visits, ngames_local, actor, device, nn_mode)
         else:
             ctx.set_weights(actor, 0)
-        res, stats, out = ctx.selfplay(visits, ngames_local, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None)
+        pinned = ctx.pinned_samples() if (buffer is not None and not own and ctx.ngames >= ngames_local) else None
+        res, stats, out = ctx.selfplay(visits, ngames_local, cpuct=cpuct, noise=noise, seed=seed, uid_base=uid_base, want_samples=buffer is not None, out=pinned)
     if world > 1:
         dev = f"cuda:{device}" if backend == "nccl" else None
         if buffer is not None:
-            out = gather_samples({k: out[k] for k in ("state", "policy", "player", "value", "fstate")}, device=dev)
+            out = gather_samples({k: out[k] for k in ("state", "policy", "player", "value", "fstate")}, device=dev, reuse_buffers=True)
         keys = ("sims", "positions", "plies", "total_length", "faults", "kernel_launches")
         tot = _sum_over_ranks(list(res) + [stats[k] for k in keys], dev)
         res = np.asarray(tot[:3], np.int64)

@@ -32,10 +32,27 @@ def reduce_max_sum(max_vals, sum_vals, device=None):
     return [float(x) for x in t.tolist()], [float(x) for x in w.tolist()]
 
 
-def gather_samples(samples: Dict[str, np.ndarray], device=None, dst: Optional[int] = None) -> Optional[Dict[str, np.ndarray]]:
+_PINNED_CACHE: Dict[tuple, "object"] = {}
+
+
+def _pinned_rows(key, rows, tail_shape, dtype):
+    """A page-locked host tensor of at least `rows` rows, cached per (field, row shape, dtype)."""
+    import torch
+    ck = (key, tuple(tail_shape), dtype)
+    t = _PINNED_CACHE.get(ck)
+    if t is None or t.shape[0] < rows:
+        t = torch.empty((max(rows, 1),) + tuple(tail_shape), dtype=dtype, pin_memory=True)
+        _PINNED_CACHE[ck] = t
+    return t
+
+
+def gather_samples(samples: Dict[str, np.ndarray], device=None, dst: Optional[int] = None, reuse_buffers: bool = False) -> Optional[Dict[str, np.ndarray]]:
     """All ranks contribute their sample block (dict of arrays with equal leading length); every rank (dst=None) or only `dst`
     receives the concatenation in rank order — which, with block-partitioned uids, is ascending game uid within each rank block.
-    Variable lengths: counts are all-gathered first, blocks are padded to the maximum for one all_gather per field."""
+    Variable lengths: counts are all-gathered first, blocks are padded to the maximum for one all_gather per field.
+
+    device (NCCL): one H2D copy, one all_gather_into_tensor, one on-device compaction and one D2H copy into a page-locked buffer per field.
+    reuse_buffers=True returns views of those cached buffers (valid until the next call) instead of copies."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
@@ -46,16 +63,26 @@ def gather_samples(samples: Dict[str, np.ndarray], device=None, dst: Optional[in
     counts[rank] = n
     dist.all_reduce(counts, op=dist.ReduceOp.SUM)
     counts_l = [int(c) for c in counts.tolist()]
-    nmax = max(counts_l)
+    nmax, total = max(counts_l), sum(counts_l)
     out = {}
     for key, arr in samples.items():
         t = torch.from_numpy(np.ascontiguousarray(arr))
-        pad = torch.zeros((nmax,) + tuple(t.shape[1:]), dtype=t.dtype)
-        pad[:n] = t
+        tail = tuple(t.shape[1:])
         if device is not None:
-            pad = pad.to(device)
+            dev_in = torch.empty((nmax,) + tail, dtype=t.dtype, device=device)      # rows beyond n are never read back
+            dev_in[:n].copy_(t, non_blocking=True)
+            dev_out = torch.empty((world * nmax,) + tail, dtype=t.dtype, device=device)
+            dist.all_gather_into_tensor(dev_out, dev_in)
+            if dst is None or dst == rank:
+                comp = torch.cat([dev_out[r * nmax:r * nmax + c] for r, c in enumerate(counts_l)], dim=0) if total else dev_out[:0]
+                host = _pinned_rows(key, total, tail, t.dtype)[:total]
+                host.copy_(comp)
+                out[key] = host.numpy() if reuse_buffers else host.numpy().copy()
+            continue
+        pad = torch.zeros((nmax,) + tail, dtype=t.dtype)
+        pad[:n] = t
         bufs = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(bufs, pad)
         if dst is None or dst == rank:
-            out[key] = np.concatenate([b[:c].cpu().numpy() for b, c in zip(bufs, counts_l)], axis=0)
+            out[key] = np.concatenate([b[:c].numpy() for b, c in zip(bufs, counts_l)], axis=0)
     return out if (dst is None or dst == rank) else None

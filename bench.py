@@ -323,18 +323,19 @@ def main():
                       "scaling": "strong"}
             # one generation end to end INCLUDING the sample gather over the ranks (NCCL all_gather of the padded blocks when world > 1)
             if world > 1:                                                        # communicator set-up and allocator warm-up are not part of a generation
-                parallel.gather_samples({kk: bufs[kk][:1024] for kk in ("state", "policy", "player", "value", "fstate")}, device="cuda")
+                parallel.gather_samples({kk: bufs[kk] for kk in ("state", "policy", "player", "value", "fstate")}, device="cuda", reuse_buffers=True)
             sync()
             t0g = time.perf_counter()
             ctx.set_weights(net)
             _, gst, gsmp = ctx.selfplay(ROLLOUT, gl, cpuct=CPUCT, seed=0, uid_base=rank * gl, out=bufs)
             t1g = time.perf_counter()
-            gathered = parallel.gather_samples({kk: gsmp[kk] for kk in ("state", "policy", "player", "value", "fstate")}, device="cuda" if world > 1 else None)
+            gathered = parallel.gather_samples({kk: gsmp[kk] for kk in ("state", "policy", "player", "value", "fstate")}, device="cuda" if world > 1 else None,
+                                               reuse_buffers=True)
             sync()
             t2g = time.perf_counter()
             (gwall, ggather), (gsims,) = parallel.reduce_max_sum([t2g - t0g, t2g - t1g], [gst["sims"]], device="cuda" if world > 1 else None)
             gen_e2e = {"workload": WORKLOAD, "total_games": GAMES, "value": gsims / gwall, "unit": "sims/s", "ms_per_step": 1e3 * gwall, "gather_ms": 1e3 * ggather,
-                       "gathered_samples": int(len(gathered["player"])), "gather": "nccl all_gather of padded per-rank blocks" if world > 1 else "single rank: none"}
+                       "gathered_samples": int(len(gathered["player"])), "gather": "nccl all_gather_into_tensor of padded per-rank blocks, compacted on the device, one D2H into page-locked memory per field" if world > 1 else "single rank: none"}
         except Exception as e:                                                   # pragma: no cover
             stage(f"strong-scaling / gather leg failed: {e!r}")
             strong = strong or {"error": repr(e)}

@@ -227,6 +227,13 @@ int agpu_get_kernel_times(agpu_ctx* ctx, agpu_kernel_times* out, int32_t reset);
 /* bytes of one node record / one game tree in HBM for this configuration */
 int agpu_layout_info(agpu_ctx* ctx, int64_t* node_bytes, int64_t* game_bytes, int64_t* lanes_per_game);
 
+/* Page-locked host memory for the caller's sample arrays (agpu_samples): with page-locked destinations agpu_selfplay streams the rows of
+ * every ply out while the next ply searches, and the final copies run at the speed of the link (B200: 96 MB in 2 ms; pageable arrays
+ * take 25 ms).  Any host language can bind these two instead of a CUDA runtime of its own.  The reference keeps its samples in ordinary
+ * Julia vectors (main4IARow.jl:29-47); the glue allocates once per context and copies into its PoolSample. */
+int agpu_host_alloc(void** out, uint64_t bytes);
+int agpu_host_free(void* p);
+
 #ifdef __cplusplus
 }
 #endif

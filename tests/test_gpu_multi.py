@@ -108,3 +108,19 @@ def test_mcts_entry_point_with_ngpus():
     o2 = ag.mcts(pnet, 8, 200, b2, spec=spec, cpuct=1.5, seed=4, ngpus=2)
     assert o1["valid"] and o2["valid"] and b1.length_buffer() == b2.length_buffer()
     assert np.array_equal(o1["stats"]["results"], o2["stats"]["results"])
+
+
+def test_pinned_sample_buffers_stream_the_same_samples():
+    """Context.pinned_samples() (agpu_host_alloc): with page-locked destinations agpu_selfplay streams every ply's rows out while the
+    next ply searches; the arrays must equal the ones returned through ordinary (pageable) numpy arrays."""
+    import alphagpu_b200 as ag
+    spec = ag.GameSpec.named("connect4")
+    net = ag.ressimplesf(2 * spec.VectorizedState, spec.maxActions, 128, 6, seed=3)
+    ctx = ag.Context(spec, 32, 700, 128, 6)
+    ctx.set_weights(net)
+    res_a, st_a, smp_a = ctx.selfplay(32, 700, cpuct=1.5, seed=12, uid_base=9)
+    res_b, st_b, smp_b = ctx.selfplay(32, 700, cpuct=1.5, seed=12, uid_base=9, out=ctx.pinned_samples())
+    assert np.array_equal(res_a, res_b) and st_a["positions"] == st_b["positions"]
+    for k in ("state", "policy", "player", "value", "fstate", "game", "ply"):
+        assert np.array_equal(smp_a[k], np.array(smp_b[k])), k
+    ctx.close()
