@@ -235,7 +235,7 @@ struct EngineT : EngineBase {
     if (const char* e = getenv("AGPU_STREAM_SAMPLES")) stream_samples = atoi(e) != 0;
     AG_CK(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     L_cap = cfg.max_games; R = cfg.rollouts;
-    AG_CK(tree.ensure((size_t)L_cap * R * Lay::REC));
+    AG_CK(tree.ensure((size_t)L_cap * Lay::game_bytes(R)));
     AG_CK(nnodes.ensure(L_cap)); AG_CK(leaf.ensure(L_cap)); AG_CK(uid.ensure(L_cap)); AG_CK(uid_b.ensure(L_cap));
     AG_CK(policy_final.ensure((size_t)L_cap * A)); AG_CK(nn_out.ensure((size_t)L_cap * Lay::OUTS));
     AG_CK(st_a.ensure(L_cap)); AG_CK(st_b.ensure(L_cap)); AG_CK(alive.ensure(L_cap));
@@ -246,11 +246,11 @@ struct EngineT : EngineBase {
     AG_CK(cudaMallocHost((void**)&total_host, sizeof(int32_t)));
     AG_CK(cudaMallocHost((void**)&fault_host, sizeof(unsigned long long)));
     AG_CK(cudaMallocHost((void**)&tallies_host, 8 * sizeof(unsigned long long)));
-    AG_CK(cudaMemsetAsync(tree.p, 0, (size_t)L_cap * R * Lay::REC, stream));
+    AG_CK(cudaMemsetAsync(tree.p, 0, (size_t)L_cap * Lay::game_bytes(R), stream));
     AG_CK(cudaMemsetAsync(policy_final.p, 0, (size_t)L_cap * A * sizeof(float), stream));
     AG_CK(cudaMemsetAsync(nn_out.p, 0, (size_t)L_cap * Lay::OUTS * sizeof(float), stream));
     AG_CK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned long long), stream));
-    P.tree = tree.p; P.game_stride = (size_t)R * Lay::REC; P.R = R; P.nnodes = nnodes.p; P.leaf = leaf.p; P.uid = uid.p;
+    P.tree = tree.p; P.game_stride = Lay::game_bytes(R); P.R = R; P.nnodes = nnodes.p; P.leaf = leaf.p; P.uid = uid.p;
     P.policy_final = policy_final.p; P.nn_out = nn_out.p; P.counters = nullptr;
     P.path_node = path_node.p; P.path_move = path_move.p; P.path_len = path_len.p;
     if (const char* e = getenv("AGPU_SEGMENTS")) nseg = atoi(e);
@@ -333,7 +333,7 @@ struct EngineT : EngineBase {
   static int blocks_for_threads(int64_t n) { return (int)((n + 255) / 256); }
 
   NNInput nn_input_tree() const {
-    NNInput I; I.tree = tree.p; I.game_stride = P.game_stride; I.rec = Lay::REC; I.off_state = Lay::OFF_STATE; I.nc = G::Geo::NC; I.VS = G::VS;
+    NNInput I; I.tree = tree.p; I.game_stride = P.game_stride; I.rec = Lay::STATE_STRIDE; I.off_state = (int)Lay::state_off(R, 0); I.nc = G::Geo::NC; I.VS = G::VS;
     I.leaf = leaf.p; I.x_direct = nullptr; I.seg = nullptr;
     return I;
   }
@@ -705,7 +705,7 @@ struct EngineT : EngineBase {
   int get_tree(int64_t L, agpu_tree_dump* out) override {
     AG_REQUIRE(out && L >= 1 && L <= L_live, AGPU_ERR_INVALID, "bad arguments");
     AG_CK(cudaSetDevice(cfg.device));
-    std::vector<char> h((size_t)L * R * Lay::REC);
+    std::vector<char> h((size_t)L * Lay::game_bytes(R));
     std::vector<int32_t> nn(L);
     AG_CK(cudaMemcpyAsync(h.data(), tree.p, h.size(), cudaMemcpyDeviceToHost, stream));
     AG_CK(cudaMemcpyAsync(nn.data(), nnodes.p, sizeof(int32_t) * L, cudaMemcpyDeviceToHost, stream));
@@ -714,7 +714,8 @@ struct EngineT : EngineBase {
       if (out->nnodes) out->nnodes[g] = nn[g];
       for (int nd = 0; nd < R; nd++) {
         const size_t o = (size_t)g * R + nd;
-        const char* rec = h.data() + o * Lay::REC;
+        const char* gbase_h = h.data() + (size_t)g * Lay::game_bytes(R);
+        const char* rec = gbase_h + (size_t)nd * Lay::REC;
         const bool live = nd < nn[g];
         NodeHdr hd; memcpy(&hd, rec + Lay::OFF_HDR, sizeof(hd));
         if (out->parent) out->parent[o] = live ? hd.parent : 0;
@@ -722,7 +723,7 @@ struct EngineT : EngineBase {
         if (out->nchild) out->nchild[o] = live ? hd.nchild : 0;
         if (out->expanded) out->expanded[o] = live ? ((hd.flags & F_EXPANDED) ? 1 : 0) : 0;
         if (out->states) {
-          if (live) { State st; memcpy(&st, rec + Lay::OFF_STATE, sizeof(st)); to_wire<G>(st, (char*)out->states + o * G::WIRE_BYTES); }
+          if (live) { State st; memcpy(&st, gbase_h + Lay::state_off(R, nd), sizeof(st)); to_wire<G>(st, (char*)out->states + o * G::WIRE_BYTES); }
           else memset((char*)out->states + o * G::WIRE_BYTES, 0, G::WIRE_BYTES);
         }
         // prior is only defined once a node was expanded (the reference zero-fills; terminal/unexpanded nodes report 0)
@@ -926,7 +927,7 @@ struct EngineT : EngineBase {
   }
   int layout_info(int64_t* node_bytes, int64_t* game_bytes, int64_t* lanes) override {
     if (node_bytes) *node_bytes = Lay::REC;
-    if (game_bytes) *game_bytes = (int64_t)R * Lay::REC;
+    if (game_bytes) *game_bytes = (int64_t)Lay::game_bytes(R);
     if (lanes) *lanes = Lay::W;
     return AGPU_OK;
   }

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   const u32 my_uid = has_game ? P.uid[my_g] : 0u;
   int my_nn = has_game ? P.nnodes[my_g] : 0;
   if (has_game) {
-    SH.root[my_gl] = *reinterpret_cast<const State*>(P.tree + (size_t)my_g * P.game_stride + Lay::OFF_STATE);
+    SH.root[my_gl] = *reinterpret_cast<const State*>(P.tree + (size_t)my_g * P.game_stride + Lay::state_off(P.R, 0));
     SH.rnd[my_gl] = philox4x32_10(my_uid, S.ply, 0u, 0u, (u32)S.seed, (u32)(S.seed >> 32));
     SH.d[my_gl] = 0;
     SH.ovf[my_gl] = 0;

@@ -31,7 +31,7 @@ struct NetDev {
 struct NNInput {
   const char* tree;        // node records, or null when x_direct is used
   size_t game_stride;
-  int rec, off_state, nc;  // record size, state offset, 64-bit chunks per board
+  int rec, off_state, nc;  // stride between the states of consecutive nodes of a game, offset of node 0's state in the game's block, 64-bit chunks per board
   int VS;
   const int32_t* leaf;     // [L] 0-based node per game
   const float* x_direct;   // [L][2VS] already encoded (agpu_forward)

@@ -96,14 +96,19 @@ struct Layout {
   static constexpr int a16(int x) { return (x + 15) / 16 * 16; }
   // FAST record: what the descent reads (header, child ids, π̄) sits in the first 64 bytes, so one 64-byte-aligned sector pair
   // serves a level of the descent; the backup's lane reads the rest.  Other layouts: prior | q | visits | child | order | state | header.
+  // Records with the order in the header and the visits in the vectors need neither array, and keep the node's STATE outside the record
+  // (SPLIT_STATE: the states of a game follow its R records) — nothing on the hot path reads a stored state: header + child ids |
+  // π̄ | prior | q = 112 bytes, ONE 128-byte line per node (192 bytes before: five sectors per backup item instead of four, a third
+  // more tree per game in L1 / L2).
+  static constexpr bool SPLIT_STATE = ORD_IN_HDR;
   static constexpr int OFF_HDR_F = 0;
   static constexpr int OFF_CHILD_F = 8;
   static constexpr int OFF_POLICY_F = a16(8 + APAD);
-  static constexpr int OFF_ORDER_F = OFF_POLICY_F + 4 * APAD;
-  static constexpr int OFF_VIS_F = a16(OFF_ORDER_F + APAD);
-  static constexpr int OFF_PRIOR_F = a16(OFF_VIS_F + 2 * APAD);
+  static constexpr int OFF_ORDER_F = OFF_POLICY_F + 4 * APAD;                                   // (unused with ORD_IN_HDR)
+  static constexpr int OFF_VIS_F = a16(OFF_ORDER_F + APAD);                                     // (unused with VIS_IN_PAD)
+  static constexpr int OFF_PRIOR_F = SPLIT_STATE ? OFF_POLICY_F + 4 * APAD : a16(OFF_VIS_F + 2 * APAD);
   static constexpr int OFF_Q_F = OFF_PRIOR_F + 4 * APAD;
-  static constexpr int OFF_STATE_F = (OFF_Q_F + 4 * APAD + 7) / 8 * 8;
+  static constexpr int OFF_STATE_F = (OFF_Q_F + 4 * APAD + 7) / 8 * 8;                          // (end of the statistics; the state itself only if !SPLIT_STATE)
 
   static constexpr int OFF_PRIOR = FAST ? OFF_PRIOR_F : 0;
   static constexpr int OFF_Q = FAST ? OFF_Q_F : 4 * APAD;
@@ -119,8 +124,15 @@ struct Layout {
   // visited level — prior_rem = Σ prior over the actions without a child (ascending action order, mcts_gpu.jl:122-124; it changes only
   // when a child is created), #{prior > 0} (:128-130; fixed by expand) and Σ visits (:118-120; +1 per backup through the node).
   static constexpr int OFF_AUX = OFF_HDR + 8;
-  static constexpr int REC = FAST ? (OFF_STATE + (int)sizeof(typename G::State) + 63) / 64 * 64
-                                  : (OFF_AUX + 8 + 31) / 32 * 32;     // record size
+  static constexpr int REC = SPLIT_STATE ? (OFF_STATE + 63) / 64 * 64
+                             : FAST ? (OFF_STATE + (int)sizeof(typename G::State) + 63) / 64 * 64
+                                    : (OFF_AUX + 8 + 31) / 32 * 32;     // record size
+  // bytes of one game's block for R nodes, and where the state of a node lives inside it
+  static constexpr int STATE_STRIDE = SPLIT_STATE ? ((int)sizeof(typename G::State) + 15) / 16 * 16 : REC;   // (16-byte aligned: state_store)
+  static constexpr size_t game_bytes(int R) { return (size_t)R * (REC + (SPLIT_STATE ? STATE_STRIDE : 0)); }
+  static constexpr size_t state_off(int R, int node) {
+    return SPLIT_STATE ? (size_t)R * REC + (size_t)node * STATE_STRIDE : (size_t)node * REC + OFF_STATE;
+  }
   static constexpr int OUTS = (A + 1 + 3) / 4 * 4;                 // floats per game of network output: logits[A], value
   static_assert(sizeof(typename G::State) % 8 == 0, "state alignment");
 };
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(256) root_reset_kernel(SearchParams P, int L, 
   int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= L) return;
   char* rec = P.tree + (size_t)g * P.game_stride;
-  if (src) *reinterpret_cast<typename G::State*>(rec + Lay::OFF_STATE) = src[g];
+  if (src) *reinterpret_cast<typename G::State*>(rec + Lay::state_off(P.R, 0)) = src[g];
   if (uid) P.uid[g] = uid[g];
   // zero the statistics (prior, q, visits, child, order, π̄)
   for (int o = Lay::STATS_BEGIN; o < Lay::STATS_END; o += 8) *reinterpret_cast<uint2*>(rec + o) = make_uint2(0, 0);
@@ -611,7 +623,7 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
       nn += 1;
       c = nn;
       if (l == best % W) *reinterpret_cast<uint8_t*>(rec + Lay::OFF_CHILD + best) = (uint8_t)c;
-      const typename G::State ps = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+      const typename G::State ps = *reinterpret_cast<const typename G::State*>(gbase + Lay::state_off(P.R, node));
       const typename G::State ns = G::play(ps, best + 1);
       int res = 0;
       const bool term = G::is_over(ns, res);
@@ -643,7 +655,7 @@ AG_D void select_game(const SearchParams& P, const int g, const int l, const uns
           *reinterpret_cast<uint8_t*>(rec + Lay::OFF_ORDER + h.nchild) = (uint8_t)(best + 1);
           reinterpret_cast<NodeHdr*>(rec + Lay::OFF_HDR)->nchild = (uint8_t)(h.nchild + 1);
         }
-        *reinterpret_cast<typename G::State*>(nrec + Lay::OFF_STATE) = ns;
+        *reinterpret_cast<typename G::State*>(gbase + Lay::state_off(P.R, c - 1)) = ns;
         hdr_store(nrec + Lay::OFF_HDR, hdr_word(node + 1, best + 1, 0, term ? F_TERMINAL : 0, res));
       }
       node = c - 1;
@@ -693,7 +705,7 @@ AG_D LeafEval expand_game(const SearchParams& P, const int g, const int l, const
   const int leaf = P.leaf[g];
   char* rec = gbase + (size_t)leaf * REC;
   const NodeHdr h = *reinterpret_cast<const NodeHdr*>(rec + Lay::OFF_HDR);
-  const typename G::State st = *reinterpret_cast<const typename G::State*>(rec + Lay::OFF_STATE);
+  const typename G::State st = *reinterpret_cast<const typename G::State*>(gbase + Lay::state_off(P.R, leaf));
   const bool term = (h.flags & F_TERMINAL) != 0;
   float v = 0.f;
 
@@ -1060,7 +1072,7 @@ AG_D void select_game1(const SearchParams& P, const int g, const int gl, const R
       for (int k = 0; k < AP / 8; k++) *reinterpret_cast<uint2*>(nrec + Lay::OFF_CHILD + 8 * k) = make_uint2(0, 0);
       hdr_store(nrec + Lay::OFF_HDR, nhw);
     }
-    state_store(nrec + Lay::OFF_STATE, ns);
+    state_store(gbase + Lay::state_off(P.R, c - 1), ns);
     if (CACHE) {
       if (unsigned char* csl = node_cache_slot<G, CACHE>(SH, gl, node)) {              // the parent's entry: child id, child count, order
         if (Lay::ORD_IN_HDR) *reinterpret_cast<uint4*>(csl) = phc;
@@ -1346,7 +1358,7 @@ __global__ void encode_nodes_kernel(SearchParams P, int L, int use_leaf, float* 
   if (t >= (size_t)L * F) return;
   int g = (int)(t / F), j = (int)(t % F);
   int node = use_leaf ? P.leaf[g] : 0;
-  const typename G::State* st = reinterpret_cast<const typename G::State*>(P.tree + (size_t)g * P.game_stride + (size_t)node * Lay::REC + Lay::OFF_STATE);
+  const typename G::State* st = reinterpret_cast<const typename G::State*>(P.tree + (size_t)g * P.game_stride + Lay::state_off(P.R, node));
   batch[t] = enc_bit<G>(*st, j) ? 1.f : 0.f;
 }
 
@@ -1421,7 +1433,7 @@ __global__ void __launch_bounds__(256) finish_ply_kernel(SearchParams P, int L, 
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   bool alive = false;
   if (g < L) {
-    const State st = *reinterpret_cast<const State*>(P.tree + (size_t)g * P.game_stride + Lay::OFF_STATE);
+    const State st = *reinterpret_cast<const State*>(P.tree + (size_t)g * P.game_stride + Lay::state_off(P.R, 0));
     const u32 uid = P.uid[g];
     const float* pol = P.policy_final + (size_t)g * A;
     if (!DUEL) {                                                                        // push_buffer (main4IARow.jl:49-63)
