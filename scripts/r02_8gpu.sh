@@ -2,7 +2,7 @@
 # round 2: the bench contract at 8 and 4 GPUs of one box (torchrun, one rank per GPU) + the single-process multi-device call
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-T=r03s
+T=r03w
 nvidia-smi -L > gpurun_out/${T}_gpus.txt
 for n in 8 4; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2951$n bench.py --gpus $n --steps 3 --warmup 3 > gpurun_out/${T}_bench_${n}gpu.json 2> gpurun_out/${T}_bench_${n}gpu.err; tail -c 400 gpurun_out/${T}_bench_${n}gpu.json; echo
