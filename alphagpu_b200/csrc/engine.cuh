@@ -264,10 +264,12 @@ struct EngineT : EngineBase {
     if (is_tc()) AG_CK(tc_init());
     if constexpr (FUSED_OK) {
       if (is_tc() && cfg.width == tc::TC_N) {
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 2>::SMEM));
-        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 2>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 1>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 0>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 1, 0>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 2, 0>::SMEM));
+        AG_CK(cudaFuncSetAttribute(fused::ply_kernel<G, 1, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fused::FCfg<G, 2, 0>::SMEM));
         use_fused = true;
         if (const char* e = getenv("AGPU_FUSED")) use_fused = atoi(e) != 0;
         if (const char* e = getenv("AGPU_FUSED_MIN_GPC")) fused_min_gpc = atoi(e);
@@ -302,14 +304,21 @@ struct EngineT : EngineBase {
       const int grid = (int)((L + gpc - 1) / gpc);
       const int fmt = tc_fmt();
       launch(K_OTHER, [&] {
-        if (gpc <= 128) {
-          // the tail of a generation: at most one tile per CTA -> the small-batch kernel (swapped orientation up to 64 games, node cache)
-          if (fmt == 0) fused::ply_kernel<G, 0, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 1><<<grid, fused::FCfg<G, 1>::THREADS, fused::FCfg<G, 1>::SMEM, stream>>>(P, T, S, visits, gpc);
+        if (gpc <= 64) {
+          // the tail of a generation: the small-batch kernel in the swapped orientation (weights resident in tensor memory, node cache)
+          typedef fused::FCfg<G, 1, 1> C1;
+          if (fmt == 0) fused::ply_kernel<G, 0, 1, 1><<<grid, C1::THREADS, C1::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1, 1><<<grid, C1::THREADS, C1::SMEM, stream>>>(P, T, S, visits, gpc);
+        } else if (gpc <= 128) {
+          // one 128-row tile per CTA, ordinary orientation, all 16 warps on it (node cache)
+          typedef fused::FCfg<G, 1, 0> C1;
+          if (fmt == 0) fused::ply_kernel<G, 0, 1, 0><<<grid, C1::THREADS, C1::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 1, 0><<<grid, C1::THREADS, C1::SMEM, stream>>>(P, T, S, visits, gpc);
         } else {
-          // two 128-row tiles per CTA, served alternately by all 16 warps
-          if (fmt == 0) fused::ply_kernel<G, 0, 2><<<grid, fused::FCfg<G, 2>::THREADS, fused::FCfg<G, 2>::SMEM, stream>>>(P, T, S, visits, gpc);
-          else fused::ply_kernel<G, 1, 2><<<grid, fused::FCfg<G, 2>::THREADS, fused::FCfg<G, 2>::SMEM, stream>>>(P, T, S, visits, gpc);
+          // two 128-row tiles per CTA, 8 warps each
+          typedef fused::FCfg<G, 2, 0> C2;
+          if (fmt == 0) fused::ply_kernel<G, 0, 2, 0><<<grid, C2::THREADS, C2::SMEM, stream>>>(P, T, S, visits, gpc);
+          else fused::ply_kernel<G, 1, 2, 0><<<grid, C2::THREADS, C2::SMEM, stream>>>(P, T, S, visits, gpc);
         }
       });
       AG_CK(cudaGetLastError());

@@ -39,7 +39,10 @@ using namespace tc;
 // memory the second tile would have used.  Both stream the weights through a 2-stage ring: the two-tile kernel then needs 162 KB of
 // shared memory, which leaves the SM 92 KB of L1 for the tree records instead of the 60 KB a third stage left (B200: -1 % per
 // generation; the search phases live on the number of load/store requests and on where they hit, see search.cuh).
-template <class G, int NT> struct FCfg {
+// SW = 1: the swapped kernel (one tile, at most 64 games per CTA).  SW = 0: ordinary orientation — every layer takes its A operand from
+// tensor memory, so shared memory only holds the network's outputs of a tile, not its 32 KB activation image.
+template <class G, int NT, int SW> struct FCfg {
+  static_assert(SW == 0 || NT == 1, "the swapped orientation is a one-tile kernel");
   static constexpr int THREADS = 512;
   static constexpr int WPT = 16 / NT;                                  // warps per tile
   static constexpr int CPW = 16 / WPT;                                 // 32-column slices per warp
@@ -48,12 +51,18 @@ template <class G, int NT> struct FCfg {
   static constexpr int PER_GAME = 2 * (int)sizeof(typename G::State) + 16 + 8 + 4 + 2 * ITEMS_PER_GAME + 2 + 2 * PATH_SMEM_DEPTH;
   static constexpr int WORK = 1024 + GAMES * ((PER_GAME + 15) / 16 * 16);   // barriers, counters, biases + the per-game hand-off
   static constexpr int TREE_BYTES = NT == 1 ? 64 * 1024 : 0;
-  static constexpr int SMEM = NT * TC_A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
+  static constexpr int OUT_BYTES = (TC_TILE_M * Layout<G>::OUTS * 4 + 1023) / 1024 * 1024;   // the network's outputs of one tile
+  static constexpr int A_BYTES = SW ? TC_A_BYTES : OUT_BYTES;          // per tile: activation image (+ outputs parked in it) or the outputs alone
+  static constexpr int SMEM = NT * A_BYTES + STAGES * TC_W_STAGE_BYTES + 1024 + WORK + TREE_BYTES;   // + 1 KB alignment slack
   // tensor memory: 128 accumulator columns per tile (the fp32 residual stream is in registers); the small-batch kernel, in the swapped
   // orientation, keeps the trunk weights — the A operand there — resident in columns 64..511 (TW_COL0 + 64 per layer)
   static constexpr int TMEM_COLS = 512;
   static constexpr int TW_COL0 = 64, TW_MAX_LAYERS = 7;
   static_assert(SMEM <= 227 * 1024, "shared memory per CTA");
+  // the carve-out steps of the SM (…, 100, 132, 164, 196, 228 KB; 1 KB of each CTA is reserved): the search phases live on the L1 that is
+  // left — one step more cost the two-tile kernel 8 % per full-load ply when it happened
+  static_assert(NT != 2 || SMEM + 1024 <= 132 * 1024, "two-tile kernel: stay inside the 132 KB shared-memory carve-out");
+  static_assert(NT != 1 || SW != 0 || SMEM + 1024 <= 164 * 1024, "one-tile ordinary kernel: stay inside the 164 KB carve-out");
 };
 
 AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
@@ -64,6 +73,11 @@ AG_D void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
       : "memory");
 }
 AG_D void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+AG_D void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 AG_D void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
@@ -98,43 +112,41 @@ AG_D void epilogue_swapped(uint32_t tmem_acc, int wq, int cs, int lane, unsigned
 
 // Epilogue of a trunk layer in the ordinary orientation: row r = 32*wq + lane of the tile, NSL consecutive 32-column slices from cs0.
 // b = relu(acc) (base layer) or b + relu(acc); the fp32 residual stream stays in this thread's registers for the whole chain (res: it
-// owns the same row and columns in every layer; they are dead registers of the search phases); next A operand = fp16/bf16(b).
+// owns the same row and columns in every layer; they are dead registers of the search phases); next A operand = fp16/bf16(b), written
+// to TENSOR memory: in the ordinary orientation every layer is tcgen05.mma with A from TMEM.  With both operands in shared memory an
+// M128 x N128 x K16 step is bound by the 8 KB it reads from there (~120 cycles per step measured, against 64 of tensor time); with A
+// from tensor memory the shared-memory side only delivers the 4 KB of weights.
 // The tensor-memory loads of a 16-column chunk are issued before the previous chunk is processed (tcgen05.wait::ld waits for ALL
 // outstanding loads, so without this the load latency is exposed once per chunk: 4 or 8 times per layer).
 template <int FMT, int NSL>
-AG_D void epilogue_ordinary(uint32_t tmem_acc, int wq, int cs0, int lane, unsigned char* At, f32x2 (&res)[16 * NSL]) {
-  const int r = wq * 32 + lane;
-  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16) + (uint32_t)(cs0 * 32);
+AG_D void epilogue_ordinary(uint32_t tmem_acc, uint32_t tmem_a, int wq, int cs0, f32x2 (&res)[16 * NSL]) {
+  const uint32_t lane_sel = ((uint32_t)(wq * 32) << 16);
+  const uint32_t acc0 = tmem_acc + lane_sel + (uint32_t)(cs0 * 32);
+  const uint32_t a0 = tmem_a + lane_sel + (uint32_t)(cs0 * 16);          // two operands per 32-bit column
   constexpr int NCH = 2 * NSL;                                          // 16-column chunks
   const f32x2 half2 = pack2f(0.5f, 0.5f);
   uint32_t va[2][16];
-  tmem_ld16(tmem_acc + lane_sel, va[0]);
+  tmem_ld16(acc0, va[0]);
 #pragma unroll
   for (int i = 0; i < NCH; i++) {
     const int b = i & 1;
     tmem_ld_wait();                                                     // chunk i has arrived
-    if (i + 1 < NCH) tmem_ld16(tmem_acc + lane_sel + 16 * (i + 1), va[b ^ 1]);   // chunk i + 1 in flight while chunk i is processed
+    if (i + 1 < NCH) tmem_ld16(acc0 + 16 * (i + 1), va[b ^ 1]);         // chunk i + 1 in flight while chunk i is processed
     // res += relu(acc), two columns per FFMA2: a + |a| is 2 relu(a) exactly, and fma(2 relu(a), 0.5, res) rounds once, like the add — one
     // FADD per column and one packed FFMA per pair on the FMA pipe instead of an FMNMX (half-rate ALU pipe) and an FADD per column.
     // (The caller zeroes res before the base layer: no select per element is spent on l == 0.)
+    uint32_t pk[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const float a0 = __uint_as_float(va[b][2 * e]), a1 = __uint_as_float(va[b][2 * e + 1]);
-      res[8 * i + e] = fma2(pack2f(__fadd_rn(a0, fabsf(a0)), __fadd_rn(a1, fabsf(a1))), half2, res[8 * i + e]);
+      const float x0 = __uint_as_float(va[b][2 * e]), x1 = __uint_as_float(va[b][2 * e + 1]);
+      res[8 * i + e] = fma2(pack2f(__fadd_rn(x0, fabsf(x0)), __fadd_rn(x1, fabsf(x1))), half2, res[8 * i + e]);
+      float lo, hi;
+      unpack2f(res[8 * i + e], lo, hi);
+      pk[e] = pack2<FMT>(lo, hi);
     }
-#pragma unroll
-    for (int c2 = 0; c2 < 2; c2++) {
-      const int c = 4 * cs0 + 2 * i + c2;
-      uint32_t pk[4];
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        float lo, hi;
-        unpack2f(res[8 * i + 4 * c2 + e], lo, hi);
-        pk[e] = pack2<FMT>(lo, hi);
-      }
-      *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-    }
+    tmem_st8(a0 + 8 * i, pk);                                           // the next layer's A operand: row r in lane r, two operands per column
   }
+  tmem_st_wait();
 }
 
 // development trace: BAR.SYNC.DEFER_BLOCKING does not block at issue but at the next consumer, so a clock read placed right behind a
@@ -145,10 +157,10 @@ AG_D long long clock_after_barrier(const void* smem_word) {
   return clock64() + (long long)(d & 0u);
 }
 
-template <class G, int FMT, int NT>
-__global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
+template <class G, int FMT, int NT, int SW>
+__global__ void __launch_bounds__(FCfg<G, NT, SW>::THREADS, 1) ply_kernel(SearchParams P, TcArgs T, SegParams S, int visits, int gpc) {
   typedef Layout<G> Lay;
-  typedef FCfg<G, NT> C;
+  typedef FCfg<G, NT, SW> C;
   typedef typename G::State State;
   constexpr bool SMALL = NT == 1;                                      // the small-batch kernel: swapped orientation, node cache
   constexpr int W = Lay::W;
@@ -165,16 +177,17 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   // Few games per CTA (the long tail of a generation): the trunk layers run as D^T = W * X^T — out-features on the M = 128 side, the
   // NS = 32 / 64 games on the N side — so the tensor time and the epilogue shrink with the batch instead of paying for 128 rows.
   // The weight image (out x in, K-major) serves as the A operand unchanged and the activation tile as the B operand unchanged.
-  const bool swapped = SMALL && count <= 64;                           // CTA-uniform; 65..128 games keep the ordinary orientation
+  constexpr bool swapped = SW != 0;                                    // (the host launches this kernel for at most 64 games per CTA)
   const int NS = count <= 32 ? 32 : 64;
   // ... and then the weights are the A operand: resident in tensor memory for the whole ply (tcgen05.mma with A from TMEM) when the trunk
   // fits its 448 spare columns, instead of streamed through shared memory for every rollout
   const bool ts_mode = swapped && T.nlayers - 1 <= C::TW_MAX_LAYERS;
+  if (swapped && count > 64) return;                                    // (never launched that way)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* sA = smem;                                            // [NT][32 KB] activations (A operands)
-  unsigned char* sW = smem + NT * TC_A_BYTES;                          // [STAGES][32 KB] weight ring
+  unsigned char* sW = smem + NT * C::A_BYTES;                          // [STAGES][32 KB] weight ring
   uint64_t* bars = reinterpret_cast<uint64_t*>(sW + STAGES * TC_W_STAGE_BYTES);
   // bars[0..2] full, [3..5] empty, [6..7] mma_done per tile, [8] stagger (one-shot)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   // the network's outputs go where the tile's A operand lived: it is dead from the head MMA until the next rollout's encoder, and
   // the search phase reads the outputs in between
   SH.out = reinterpret_cast<float*>(sA);
-  SH.out_tile_stride = TC_A_BYTES / 4;
+  SH.out_tile_stride = C::A_BYTES / 4;
   static_assert(TC_TILE_M * Lay::OUTS * 4 <= TC_KTILE_BYTES_A, "the network's outputs live in the first K tile of the idle A tile");
   // node cache (small-batch kernel): the first nc_nodes nodes of each of this CTA's games; the fewer games, the deeper the cache
   SH.nc_base = reinterpret_cast<unsigned char*>(bars) + C::WORK;
@@ -240,8 +253,12 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
   constexpr int WPT = C::WPT, CPW = C::CPW;
   const int t = warp / WPT, wq = warp & 3, csb = ((warp >> 2) & (WPT / 4 - 1)) * CPW;
   const int r = wq * 32 + lane;
-  unsigned char* At = sA + t * TC_A_BYTES;
+  unsigned char* At = sA + t * C::A_BYTES;                             // (the activation image: swapped kernel only)
   const uint32_t tmem_acc = tmem_base + (uint32_t)(t * TC_N);
+  // ordinary orientation: the A operand (activations, 128 rows x 128 operands = 64 columns) of tile t lives in tensor memory behind the
+  // accumulators (the small-batch kernel's resident weights occupy those columns only in the swapped orientation)
+  constexpr int TA_COL0 = NT * TC_N;
+  const uint32_t tmem_a = tmem_base + (uint32_t)(TA_COL0 + 64 * t);
   // The MMA-issuing warp of a tile takes a WARP-UNIFORM branch and elects one lane inside it; every operand of tcgen05.mma is derived
   // from values the compiler can see as uniform (the broadcast warp index, the broadcast TMEM base).  Issued from a divergent
   // `lane == 0` branch each MMA went through an ELECT / 5 x R2UR / BRA.U.ANY waterfall: ~75 cycles per instruction, 600 per layer.
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
     tc_fence_after();
     if (elect_one()) {
       const uint32_t tmem_acc_u = tmem_base_u + (uint32_t)(t * TC_N);
-      const uint64_t ad0 = umma_desc(smem_u32(sA) + (uint32_t)(t * TC_A_BYTES));
+      const uint64_t ad0 = umma_desc(smem_u32(sA) + (uint32_t)(t * C::A_BYTES));
       const uint64_t bd0 = umma_desc(smem_u32(sW) + (uint32_t)(s * TC_W_STAGE_BYTES));
       const uint64_t bstep = (uint64_t)((nl * 128) >> 4);
       if (SMALL && ts_mode && !is_head) {
@@ -331,8 +348,16 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
           const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
           umma_bf16(tmem_acc_u, bd0 + binc, ad0 + ainc, idesc, ks > 0 ? 1u : 0u);   // weights as A, activations as B
         }
+      } else if (!swapped) {
+        const uint32_t idesc = umma_idesc<FMT>(nl);                     // ordinary orientation, every layer: activations (TMEM) as A, weights as B
+        const uint32_t ta = tmem_base_u + (uint32_t)(TA_COL0 + 64 * t);
+#pragma unroll
+        for (int ks = 0; ks < TC_N / 16; ks++) {
+          const uint64_t binc = (uint64_t)(((ks & 3) * 32) >> 4) + ((ks >> 2) ? bstep : 0);
+          umma_ts(tmem_acc_u, ta + (uint32_t)(8 * ks), bd0 + binc, idesc, ks > 0 ? 1u : 0u);
+        }
       } else {
-        const uint32_t idesc = umma_idesc<FMT>(nl);
+        const uint32_t idesc = umma_idesc<FMT>(nl);                     // the head layer behind a swapped trunk: both operands in shared memory
 #pragma unroll
         for (int ks = 0; ks < TC_N / 16; ks++) {
           const uint64_t ainc = (uint64_t)(((ks >> 2) * TC_KTILE_BYTES_A + (ks & 3) * 32) >> 4);
@@ -436,21 +461,29 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
       for (int j = 0; j < CPW; j++) {
         const int cs = csb + j;
         // (warp-uniform) columns beyond the input: zero weights in the base layer's image, zeros written by the first rollout, finite
-        // activations afterwards — nothing to encode.  Columns 0..63 are always rewritten: the network's outputs (fp32, any bit pattern)
-        // were parked in the first K tile.  (Skipping the K-steps in the MMA sequence instead costs far more than it saves: a branch
-        // between two tcgen05.mma stalls the issue, +2.8 ms per generation on B200.)
+        // activations afterwards — nothing to encode.  In shared memory columns 0..63 are always rewritten: the network's outputs
+        // (fp32, any bit pattern) were parked in the first K tile.  (Skipping the K-steps in the MMA sequence instead costs far more than
+        // it saves: a branch between two tcgen05.mma stalls the issue, +2.8 ms per generation on B200.)
         if (k > 0 && 32 * cs >= max(16 * T.k0_steps, 64)) continue;
         const uint32_t bits = (uint32_t)(((cs & 2) ? x1 : x0) >> (32 * (cs & 1)));
+        uint32_t w[16];                                                // the 32 operands of the slice, two per word
 #pragma unroll
         for (int i = 0; i < 4; i++) {
           const uint32_t byte = (bits >> (8 * i)) & 0xFFu;
-          uint32_t w[4];
 #pragma unroll
-          for (int e = 0; e < 4; e++) w[e] = bits2_to_operands(byte >> (2 * e), one);
-          const int c = 4 * cs + i;                                    // chunk of 8 operands in the row, 0..15
-          *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int e = 0; e < 4; e++) w[4 * i + e] = bits2_to_operands(byte >> (2 * e), one);
+        }
+        if (!swapped) {                                                // ordinary orientation: the A operand lives in tensor memory
+          tmem_st16(tmem_a + ((uint32_t)(wq * 32) << 16) + (uint32_t)(16 * cs), w);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const int c = 4 * cs + i;                                  // chunk of 8 operands in the row, 0..15
+            *reinterpret_cast<uint4*>(At + (c >> 3) * TC_KTILE_BYTES_A + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+          }
         }
       }
+      if (!swapped) { tmem_st_wait(); tc_fence_before(); }
     }
     if (t < ntiles) {                                                  // an idle tile rejoins at the end-of-rollout barrier
       fence_proxy_async();
@@ -494,7 +527,7 @@ __global__ void __launch_bounds__(FCfg<G, NT>::THREADS, 1) ply_kernel(SearchPara
             if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, At, sres);
             else epilogue_swapped<FMT, 16>(tmem_acc, wq, csb, lane, At, sres);
           } else {
-            epilogue_ordinary<FMT, CPW>(tmem_acc, wq, csb, lane, At, rres);
+            epilogue_ordinary<FMT, CPW>(tmem_acc, tmem_a, wq, csb, rres);
           }
           tc_fence_before();
           fence_proxy_async();
