@@ -175,14 +175,15 @@ __global__ void __launch_bounds__(FCfg<G, NT, SW>::THREADS, 1) ply_kernel(Search
   const int g0 = S.off + cta_first;                                    // global slot of local game 0
   const int ntiles = (NT == 2 && count > TC_TILE_M) ? 2 : 1;           // a CTA with <= 128 games runs a single tile
   // Few games per CTA (the long tail of a generation): the trunk layers run as D^T = W * X^T — out-features on the M = 128 side, the
-  // NS = 32 / 64 games on the N side — so the tensor time and the epilogue shrink with the batch instead of paying for 128 rows.
+  // NS = 32 games on the N side — so the epilogue shrinks with the batch instead of paying for 128 rows (up to 32 games per CTA; from 33
+  // on the ordinary one-tile kernel, whose A operand also lives in tensor memory, is faster: 1.17 against 1.28 ms per ply at 9 k games).
   // The weight image (out x in, K-major) serves as the A operand unchanged and the activation tile as the B operand unchanged.
-  constexpr bool swapped = SW != 0;                                    // (the host launches this kernel for at most 64 games per CTA)
-  const int NS = count <= 32 ? 32 : 64;
+  constexpr bool swapped = SW != 0;                                    // (the host launches this kernel for at most 32 games per CTA)
+  constexpr int NS = 32;
   // ... and then the weights are the A operand: resident in tensor memory for the whole ply (tcgen05.mma with A from TMEM) when the trunk
   // fits its 448 spare columns, instead of streamed through shared memory for every rollout
   const bool ts_mode = swapped && T.nlayers - 1 <= C::TW_MAX_LAYERS;
-  if (swapped && count > 64) return;                                    // (never launched that way)
+  if (swapped && count > NS) return;                                    // (never launched that way)
 
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -524,8 +525,7 @@ __global__ void __launch_bounds__(FCfg<G, NT, SW>::THREADS, 1) ply_kernel(Search
         if (ltr) { lt3 = clock64(); t_ly[0] += lt1 - lt0; t_ly[1] += lt2 - lt1; t_ly[2] += lt3 - lt2; }
         if (!is_head) {
           if (SMALL && swapped) {
-            if (NS == 32) epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, At, sres);
-            else epilogue_swapped<FMT, 16>(tmem_acc, wq, csb, lane, At, sres);
+            epilogue_swapped<FMT, 8>(tmem_acc, wq, csb, lane, At, sres);
           } else {
             epilogue_ordinary<FMT, CPW>(tmem_acc, tmem_a, wq, csb, rres);
           }
