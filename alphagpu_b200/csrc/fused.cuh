@@ -7,9 +7,12 @@
 //                  per game (select_game1).  Everything a phase hands to the next lives in shared memory (RolloutShared).
 //   network phase: the tcgen05/TMEM chain of DenseNet.jl:294-304 on the leaves, 128 games per tile.  Two tiles (129..256 games): 8 warps
 //                  per tile — TMEM lane quarter w%4, two 32-column slices each — with their own MMA issuer, tile 1 trailing tile 0 by one
-//                  MMA phase so that one tile's epilogue runs under the other's MMAs.  One tile: all 16 warps on it, one slice each.
-//                  The fp32 residual stream lives in registers (a thread owns the same row and columns in every layer); weights stream
-//                  global -> shared through a bulk-copy ring that never drains between rollouts.
+//                  MMA phase so that one tile's epilogue runs under the other's MMAs.  One tile (33..128 games): all 16 warps on it, one
+//                  slice each.  In both the A operand of every layer lives in TENSOR memory (encoder and epilogues write it with
+//                  tcgen05.st, every layer is tcgen05.mma with A from TMEM): with both operands in shared memory a K-step was bound by
+//                  the 8 KB it read there (~120 cycles against 64 of tensor time).  The fp32 residual stream lives in registers (a
+//                  thread owns the same row and columns in every layer); weights stream global -> shared through a bulk-copy ring that
+//                  never drains between rollouts.  Up to 32 games per CTA: the swapped kernel (SW = 1, below).
 //                  (Measured alternatives, B200: all 16 warps alternating between the two tiles — 32 k cycles per rollout against 25 k,
 //                  because issuing a layer's eight tcgen05.mma occupies the issuing warp for 600-1200 cycles and the other 15 wait for
 //                  its share of the epilogue; the same with a 17th, issue-only warp — the register file then holds 20 warps x 96
@@ -34,11 +37,10 @@ using namespace tc;
 #define AG_TRACE 0
 #endif
 
-// NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA).  NT = 1: the small-batch kernel of the tail of a generation
-// (<= 128 games per CTA): trunk layers in the swapped orientation up to 64 games, and a node cache (search.cuh: CacheSlot) in the shared
-// memory the second tile would have used.  Both stream the weights through a 2-stage ring: the two-tile kernel then needs 162 KB of
-// shared memory, which leaves the SM 92 KB of L1 for the tree records instead of the 60 KB a third stage left (B200: -1 % per
-// generation; the search phases live on the number of load/store requests and on where they hit, see search.cuh).
+// NT = tiles per CTA.  NT = 2: the full-load kernel (129..256 games per CTA).  NT = 1: at most 128 games per CTA, with a node cache
+// (search.cuh: CacheSlot) in the shared memory the second tile would have used.  All stream the weights through a 2-stage ring (a third
+// stage bought nothing and cost 32 KB of L1: the search phases live on the number of load/store requests and on where they hit, see
+// search.cuh).
 // SW = 1: the swapped kernel (one tile, at most 64 games per CTA).  SW = 0: ordinary orientation — every layer takes its A operand from
 // tensor memory, so shared memory only holds the network's outputs of a tile, not its 32 KB activation image.
 template <class G, int NT, int SW> struct FCfg {
