@@ -37,6 +37,8 @@ def _worker(rank, world, port, q):
         base, _ = parallel.shard_games(8, rank, world)
         smp = dict(game=np.arange(base, base + n, dtype=np.int32), policy=np.full((n, 7), rank + 0.5, np.float32), state=np.full((n, 84), rank, np.int8))
         allg = parallel.gather_samples(smp)
+        again = parallel.gather_samples(smp, reuse_buffers=True)       # (the flag only changes who owns the result on the NCCL path)
+        assert all(np.array_equal(allg[k], again[k]) for k in allg)
         only0 = parallel.gather_samples(smp, dst=0)
         empty = parallel.gather_samples(dict(game=np.zeros(0 if rank == 0 else 2, np.int32)))
         q.put((rank, mx, sm, {k: v.tolist() for k, v in allg.items()}, None if only0 is None else len(only0["game"]), empty["game"].shape[0]))
